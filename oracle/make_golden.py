@@ -1,0 +1,215 @@
+"""Generate tests/golden/*.npz by EXECUTING THE REAL REFERENCE (build container only).
+
+    python -m oracle.make_golden            # writes tests/golden/
+
+Test infrastructure.  The reference has no golden vectors of its own, so the
+pins for the oracle are outputs of the unmodified reference sources under /root/reference,
+run on CPU with fixed seeds.  Inputs are stored with the outputs so the fixtures are
+self-contained on the GPU box (where /root/reference does not exist).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from oracle.tag_oracle import make_tag_params  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def synth_features(seed: int, b: int, d: int, dtype=torch.float64):
+    """Correlated, L2-normalised image/text features (SURVEY.md §8d synthetic-input recipe)."""
+    g = torch.Generator().manual_seed(seed)
+    i_raw = torch.randn(b, d, generator=g, dtype=torch.float32)
+    noise = torch.randn(b, d, generator=g, dtype=torch.float32)
+    t_raw = 0.5 * i_raw + 0.5 * noise
+    return (F.normalize(i_raw.to(dtype), dim=-1), F.normalize(t_raw.to(dtype), dim=-1))
+
+
+# ----------------------------------------------------------------------------------------------
+def golden_clip_w1():
+    ref = ref_shim.load_ref_loss()
+    out = {}
+    cases = [(16, 32, 14.285714, 0), (48, 64, 100.0, 1), (33, 40, 1.0, 2), (128, 96, 30.0, 3)]
+    for n, (b, d, s, seed) in enumerate(cases):
+        for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+            I, T = synth_features(seed, b, d)
+            I = I.to(dt).requires_grad_(True)
+            T = T.to(dt).requires_grad_(True)
+            sc = torch.tensor(s, dtype=dt, requires_grad=True)
+            loss = ref.ClipLoss()(I, T, sc)
+            d_out = ref.ClipLoss()(I.detach(), T.detach(), sc.detach(), output_dict=True)
+            assert list(d_out.keys()) == ["contrastive_loss"]
+            loss.backward()
+            pre = f"c{n}_{tag}_"
+            out[pre + "I"] = I.detach().numpy()
+            out[pre + "T"] = T.detach().numpy()
+            out[pre + "scale"] = np.asarray(s, dtype=np.float64)
+            out[pre + "loss"] = loss.detach().numpy()
+            out[pre + "dI"] = I.grad.numpy()
+            out[pre + "dT"] = T.grad.numpy()
+            out[pre + "dscale"] = sc.grad.numpy()
+    out["n_cases"] = np.asarray(len(cases))
+    np.savez_compressed(os.path.join(OUT, "clip_w1.npz"), **out)
+    print("clip_w1.npz", len(out))
+
+
+def _dist_worker(rank, world, port, b, d, scale, seed, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ref = ref_shim.load_ref_loss()
+    res = {}
+    for local_loss in (False, True):
+        for gwg in (False, True):
+            I_all, T_all = synth_features(seed, b * world, d)
+            I = I_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+            T = T_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+            sc = torch.tensor(scale, dtype=torch.float64, requires_grad=True)
+            loss = ref.ClipLoss(local_loss=local_loss, gather_with_grad=gwg, cache_labels=True,
+                                rank=rank, world_size=world)(I, T, sc)
+            loss.backward()
+            key = f"ll{int(local_loss)}_gwg{int(gwg)}_r{rank}_"
+            res[key + "loss"] = loss.detach().numpy()
+            res[key + "dI"] = I.grad.numpy()
+            res[key + "dT"] = T.grad.numpy()
+            res[key + "dscale"] = sc.grad.numpy()
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def golden_clip_dist():
+    import torch.multiprocessing as mp
+    out = {}
+    port = 29611
+    for world, b, d, scale, seed in ((2, 6, 16, 14.285714, 10), (3, 5, 24, 60.0, 11)):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_dist_worker, args=(r, world, port, b, d, scale, seed, q))
+                 for r in range(world)]
+        for p in procs:
+            p.start()
+        got = [q.get(timeout=300) for _ in range(world)]
+        for p in procs:
+            p.join()
+        port += 1
+        pre = f"w{world}_"
+        I_all, T_all = synth_features(seed, b * world, d)
+        out[pre + "I"] = I_all.numpy()
+        out[pre + "T"] = T_all.numpy()
+        out[pre + "b"] = np.asarray(b)
+        out[pre + "scale"] = np.asarray(scale)
+        for _, res in got:
+            for k, v in res.items():
+                out[pre + k] = v
+    np.savez_compressed(os.path.join(OUT, "clip_dist.npz"), **out)
+    print("clip_dist.npz", len(out))
+
+
+def golden_l2norm():
+    g = torch.Generator().manual_seed(20)
+    x = torch.randn(9, 24, generator=g, dtype=torch.float64)
+    x[2] = 0.0                       # zero row -> eps clamp (F.normalize eps=1e-12)
+    x[5] = x[5] * 1e-14              # tiny row, also below eps
+    x[7] = x[7] * 1e4
+    x.requires_grad_(True)
+    # exactly the call in model.py:313 / :333
+    y = F.normalize(x, dim=-1)
+    gy = torch.randn(9, 24, generator=g, dtype=torch.float64)
+    y.backward(gy)
+    np.savez_compressed(os.path.join(OUT, "l2norm.npz"), x=x.detach().numpy(), y=y.detach().numpy(),
+                        gy=gy.numpy(), gx=x.grad.numpy())
+    print("l2norm.npz")
+
+
+def golden_asl():
+    asl = ref_shim.load_ref_asl()
+    out = {}
+    g = torch.Generator().manual_seed(30)
+    x = (torch.randn(7, 44, generator=g, dtype=torch.float64) * 3.0)
+    x[0, 0], x[0, 1] = 40.0, -40.0   # saturate both clamps
+    y22 = (torch.rand(7, 22, generator=g) > 0.7).to(torch.float64)
+    y = y22.repeat(1, 2)             # train_other.py:128
+    out["x"], out["y"] = x.numpy(), y.numpy()
+    for n, (gn, gp, clip) in enumerate(((4, 1, 0.05), (7, 0, 0.05), (0, 0, 0.0))):
+        xx = x.clone().requires_grad_(True)
+        loss = asl.AsymmetricLoss(gamma_neg=gn, gamma_pos=gp, clip=clip)(xx, y)
+        loss.backward()
+        assert torch.is_grad_enabled()
+        out[f"k{n}_cfg"] = np.asarray([gn, gp, clip], dtype=np.float64)
+        out[f"k{n}_loss"] = loss.detach().numpy()
+        out[f"k{n}_dx"] = xx.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "asl.npz"), **out)
+    print("asl.npz")
+
+
+def golden_tag_head():
+    oc = ref_shim.load_ref_open_clip()
+    from open_clip.model import CLIP
+    out = {}
+    cases = [  # (seed, D, b, N, gain)
+        (40, 64, 3, 50, 1.0),
+        (41, 32, 2, 7, 6.0),
+        (42, 48, 2, 197, 6.0),
+    ]
+    for n, (seed, D, b, N, gain) in enumerate(cases):
+        with ref_shim._cwd(os.path.join(ref_shim.REF_SRC, "open_clip")):
+            head, tag_labels, tag_fc = ref_shim.build_ref_tag_head(D)
+        params = make_tag_params(seed, D, gain=gain, dtype=torch.float64)
+        holder = torch.nn.Module()
+        holder.tag_head, holder.tag_labels, holder.tag_fc = head, tag_labels, tag_fc
+        holder.double()
+        missing, unexpected = holder.load_state_dict(params, strict=True)
+        holder.eval()
+        g = torch.Generator().manual_seed(seed + 1000)
+        tokens = torch.randn(b, N, D, generator=g, dtype=torch.float32).double().requires_grad_(True)
+        # the reference's own method body, unbound, on a holder carrying the reference modules
+        logits = CLIP.tag_forward(holder, tokens)
+        gl = torch.randn(b, 44, generator=g, dtype=torch.float32).double()
+        logits.backward(gl)
+        pre = f"t{n}_"
+        out[pre + "cfg"] = np.asarray([seed, D, b, N, gain], dtype=np.float64)
+        out[pre + "tokens"] = tokens.detach().numpy()
+        out[pre + "logits"] = logits.detach().numpy()
+        out[pre + "glogits"] = gl.numpy()
+        out[pre + "dtokens"] = tokens.grad.numpy()
+        out[pre + "dq0w"] = head.encoder.layer[0].crossattention.self.query.weight.grad.numpy()[:4, :8].copy()
+        out[pre + "dk1w"] = head.encoder.layer[1].crossattention.self.key.weight.grad.numpy()[:4, :8].copy()
+        # control words through the reference's own prepare_control_words
+        with open(os.path.join(ref_shim.REF_SRC, "open_clip", "tagging", "scar_tag_list.txt")) as fr:
+            tag_list = [t.strip() for t in fr.readlines()]
+        holder.tag_list = tag_list
+        words = CLIP.prepare_control_words(holder, logits.detach())
+        out[pre + "words"] = np.asarray(words)
+        out[pre + "tag_list"] = np.asarray(tag_list)
+        out[pre + "state_keys"] = np.asarray(sorted(holder.state_dict().keys()))
+    out["n_cases"] = np.asarray(len(cases))
+    np.savez_compressed(os.path.join(OUT, "tag_head.npz"), **out)
+    print("tag_head.npz")
+
+
+def main():
+    assert ref_shim.available(), "reference tree not found"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(4)
+    golden_l2norm()
+    golden_asl()
+    golden_clip_w1()
+    golden_clip_dist()
+    golden_tag_head()
+
+
+if __name__ == "__main__":
+    main()
