@@ -1,0 +1,154 @@
+/*
+ * xtag_b200.h -- C ABI of libxtag_b200.so: the B200 (sm_100a) kernels behind XTag-CLIP's
+ * data-parallel hot path (open_clip contrastive head + XTag cross-attention tag head).
+ *
+ * The reference (EJLEE5826/XTag-CLIP) is pure Python/PyTorch and has NO FFI layer of its own
+ * (SURVEY.md section 8b): the boundary it exposes is the Python API.  Each entry point below
+ * therefore names the reference *Python* interface whose arithmetic it replaces (file:line under
+ * /root/reference); the Python mirror that keeps those signatures lives in xtag_clip_b200/ and
+ * binds this library with ctypes (INTEGRATION.md shows the stub a maintainer adds).
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *     kernels never allocate: scratch is sized by *_ws_bytes() and passed in
+ *   - stream is a cudaStream_t passed as void*; calls are asynchronous and stream-ordered,
+ *     re-entrant, no global mutable state besides a thread-local last-error string
+ *   - matrices are dense row-major; dtype codes below; rows must be 16-byte aligned
+ *   - return 0 on success; XTAG_ERR_* (<0) otherwise, message via xtag_last_error()
+ *   - NO CPU fallback: without a CUDA device of compute capability 10.x every compute call
+ *     returns XTAG_ERR_CUDA.
+ */
+#ifndef XTAG_B200_H_
+#define XTAG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XTAG_ABI_VERSION 1
+
+#define XTAG_F32  0
+#define XTAG_BF16 1
+
+#define XTAG_OK               0
+#define XTAG_ERR_INVALID     -1   /* bad argument (null pointer, negative size, bad dtype)   */
+#define XTAG_ERR_UNSUPPORTED -2   /* shape / alignment / dtype combination not implemented  */
+#define XTAG_ERR_CUDA        -3   /* CUDA runtime / driver error, or no sm_100 device        */
+#define XTAG_ERR_WORKSPACE   -4   /* workspace too small                                     */
+
+/* implementation selector for the contrastive kernels */
+#define XTAG_IMPL_AUTO 0          /* bf16 + aligned shapes -> tcgen05, otherwise SIMT fp32    */
+#define XTAG_IMPL_SIMT 1          /* fp32 FFMA path (any dtype, any shape): the "fp32 mode"   */
+#define XTAG_IMPL_TC   2          /* tcgen05/TMEM/TMA path (bf16 inputs, D % 8 == 0)          */
+
+int         xtag_version(void);
+const char* xtag_last_error(void);
+/* 0 when the current device is compute capability 10.x, XTAG_ERR_CUDA otherwise */
+int         xtag_device_check(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+uint64_t    xtag_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  fused L2-normalise + cast.   Replaces F.normalize(features, dim=-1) in
+ *     CLIP.encode_image / encode_text   (src/open_clip/model.py:311-313, 332-333).
+ *     y = x / max(||x||_2, eps); inv_norm[r] = 1/max(||x_r||, eps) is saved for the backward.
+ *     yT (optional, may be NULL): the same result transposed, [dim, rows] in y_dtype.
+ *     bwd: gx = inv_norm * (gy - y (y . gy)) when ||x|| >= eps, gy * inv_norm otherwise
+ *     (the sub-gradient torch's clamp_min takes).
+ * ------------------------------------------------------------------------------------------- */
+int xtag_l2norm_fwd(const void* x, int x_dtype, void* y, int y_dtype, void* yT, float* inv_norm,
+                    int rows, int dim, float eps, void* stream);
+int xtag_l2norm_bwd(const void* gy, int gy_dtype, const void* y, int y_dtype, const float* inv_norm,
+                    void* gx, int gx_dtype, int rows, int dim, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  fused contrastive forward.   Replaces ClipLoss.get_logits + get_ground_truth +
+ *     F.cross_entropy x2   (src/open_clip/loss.py:91-139) for one row block of the logits:
+ *         S = scale * A Bm^T            A [M, D] (the rank's rows), Bm [N, D] (all columns)
+ *     without ever writing S.  Outputs (fp32, natural-log units):
+ *         row_lse[i] = LSE_j S_ij            (image->text CE of the local rows)
+ *         col_lse[j] = LSE_{i<M} S_ij        (PARTIAL over this rank's rows; combine across
+ *                                             ranks with xtag_lse_combine)
+ *         diag[i]    = S_{i, i+label_offset} (the label logit; label_offset = b*rank,
+ *                                             loss.py:95-96)
+ * ------------------------------------------------------------------------------------------- */
+size_t xtag_clip_fwd_ws_bytes(int M, int N, int D, int dtype, int impl);
+int xtag_clip_fwd(const void* A, const void* Bm, int dtype, int M, int N, int D,
+                  const float* scale /* device scalar: logit_scale.exp() */, int label_offset,
+                  float* row_lse, float* col_lse, float* diag,
+                  void* ws, size_t ws_bytes, int impl, void* stream);
+
+/* out[j] = log sum_w exp(parts[w*N + j]): merges the per-rank partial column LSEs after the
+ * all-gather (the one exchange step of the sharded loss). */
+int xtag_lse_combine(const float* parts, int W, int N, float* out, void* stream);
+
+/* loss = 0.5 * [ mean_i(row_lse_i - diag_i) + mean_i(col_lse[label_offset+i] - diag_i) ]
+ * (loss.py:134-137 with the two cross-entropies written out).  loss_out[0] is overwritten. */
+int xtag_clip_loss(const float* row_lse, const float* diag, const float* col_lse,
+                   int M, int label_offset, float* loss_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  fused contrastive backward (autograd of loss.py:116-137).  Recomputes S tile by tile and
+ *     forms   dS_ij = g * ( w_row * exp(S_ij - row_lse_i) + w_col * exp(S_ij - col_lse_j)
+ *                           - w_diag * [j == i + label_offset] )
+ *     with g = *grad_out (device scalar), then
+ *         dA = scale * dS   Bm      [M, D]   (skipped when dA == NULL)
+ *         dB = scale * dS^T A       [N, D]   (skipped when dB == NULL)
+ *         dscale[0] += sum_ij dS_ij * S_ij / scale
+ *     The weights select the reference's gradient mode (DESIGN.md "gradient modes").
+ *     dS is staged once in the workspace (bf16 on the tcgen05 path, fp32 on the SIMT path).
+ * ------------------------------------------------------------------------------------------- */
+size_t xtag_clip_bwd_ws_bytes(int M, int N, int D, int dtype, int impl);
+int xtag_clip_bwd(const void* A, const void* Bm, int dtype, int M, int N, int D,
+                  const float* scale /* device scalar */, int label_offset,
+                  const float* row_lse, const float* col_lse,
+                  float w_row, float w_col, float w_diag, const float* grad_out,
+                  void* dA, void* dB, int grad_dtype, float* dscale,
+                  void* ws, size_t ws_bytes, int impl, void* stream);
+
+/* plain tcgen05 GEMM used by K2 and exported for bring-up tests:
+ *   C[M,N] = alpha * A[M,K] * B[N,K]^T   (A, B bf16 row-major "K-major"; C f32 or bf16; alpha by value) */
+int xtag_tc_gemm_nt(const void* A, const void* B, void* C, int c_dtype,
+                    int M, int N, int K, float alpha, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  tag-head cross-attention core.  Replaces the eager attention in
+ *     BertSelfAttention.forward, cross branch (src/open_clip/tagging_heads/bert.py:219-274):
+ *         P = softmax(q k^T * softmax_scale) ; P = dropout(P) ; ctx = P v     per (sample, head)
+ *     q [b, Lq, heads*dh] (row stride ldq elements), k/v [b, Lk, heads*dh] (row strides ldk/ldv;
+ *     batch strides = L * ld), o [b, Lq, heads*dh] contiguous, lse [b, heads, Lq] fp32.
+ *     The all-ones encoder mask of tag_forward (model.py:339-341) is the additive constant 0.
+ *     dropout_p == 0 is eval mode; otherwise a Philox4x32-10 keep-mask keyed by (seed, offset).
+ * ------------------------------------------------------------------------------------------- */
+int xtag_xattn_fwd(const void* q, const void* k, const void* v, int dtype,
+                   void* o, float* lse,
+                   int b, int Lq, int Lk, int heads, int dh,
+                   int ldq, int ldk, int ldv,
+                   float softmax_scale, float dropout_p, uint64_t seed, uint64_t offset,
+                   void* stream);
+int xtag_xattn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                   const float* lse, int dtype,
+                   void* dq, void* dk, void* dv,
+                   int b, int Lq, int Lk, int heads, int dh,
+                   int ldq, int ldk, int ldv,
+                   float softmax_scale, float dropout_p, uint64_t seed, uint64_t offset,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  AsymmetricLoss forward + d/dx in one pass.  Replaces AsymmetricLoss.forward
+ *     (src/open_clip/tagging_heads/asymmetric_loss.py:16-50); focal weight carries no gradient.
+ *     loss_out[0] = -sum(loss); dx[n] (fp32) = d loss / d x for grad_out = 1 (may be NULL).
+ *     idx6 (optional): the per-category top-1 tag indices of CLIP.prepare_control_words
+ *     (src/open_clip/model.py:354-374), int32 [rows, 6]; requires cols == 44.
+ * ------------------------------------------------------------------------------------------- */
+int xtag_asl_fwd(const void* x, int x_dtype, const float* y, int rows, int cols,
+                 float gamma_neg, float gamma_pos, float clip, float eps,
+                 float* loss_out, float* dx, int32_t* idx6, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XTAG_B200_H_ */

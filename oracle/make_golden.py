@@ -27,12 +27,13 @@ from oracle.tag_oracle import make_tag_params  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def synth_features(seed: int, b: int, d: int, dtype=torch.float64):
-    """Correlated, L2-normalised image/text features (SURVEY.md §8d synthetic-input recipe)."""
+def synth_features(seed: int, b: int, d: int, dtype=torch.float64, corr: float = 0.5):
+    """Correlated, L2-normalised image/text features (SURVEY.md §8d synthetic-input recipe);
+    `corr` is lowered for the high-scale cases so the loss stays far from fp32 underflow."""
     g = torch.Generator().manual_seed(seed)
     i_raw = torch.randn(b, d, generator=g, dtype=torch.float32)
     noise = torch.randn(b, d, generator=g, dtype=torch.float32)
-    t_raw = 0.5 * i_raw + 0.5 * noise
+    t_raw = corr * i_raw + (1.0 - corr) * noise
     return (F.normalize(i_raw.to(dtype), dim=-1), F.normalize(t_raw.to(dtype), dim=-1))
 
 
@@ -40,10 +41,10 @@ def synth_features(seed: int, b: int, d: int, dtype=torch.float64):
 def golden_clip_w1():
     ref = ref_shim.load_ref_loss()
     out = {}
-    cases = [(16, 32, 14.285714, 0), (48, 64, 100.0, 1), (33, 40, 1.0, 2), (128, 96, 30.0, 3)]
-    for n, (b, d, s, seed) in enumerate(cases):
+    cases = [(16, 32, 14.285714, 0, 0.5), (48, 64, 100.0, 1, 0.12), (33, 40, 1.0, 2, 0.5), (128, 96, 30.0, 3, 0.3)]
+    for n, (b, d, s, seed, corr) in enumerate(cases):
         for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
-            I, T = synth_features(seed, b, d)
+            I, T = synth_features(seed, b, d, corr=corr)
             I = I.to(dt).requires_grad_(True)
             T = T.to(dt).requires_grad_(True)
             sc = torch.tensor(s, dtype=dt, requires_grad=True)
@@ -64,7 +65,7 @@ def golden_clip_w1():
     print("clip_w1.npz", len(out))
 
 
-def _dist_worker(rank, world, port, b, d, scale, seed, q):
+def _dist_worker(rank, world, port, b, d, scale, seed, corr, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -73,7 +74,7 @@ def _dist_worker(rank, world, port, b, d, scale, seed, q):
     res = {}
     for local_loss in (False, True):
         for gwg in (False, True):
-            I_all, T_all = synth_features(seed, b * world, d)
+            I_all, T_all = synth_features(seed, b * world, d, corr=corr)
             I = I_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
             T = T_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
             sc = torch.tensor(scale, dtype=torch.float64, requires_grad=True)
@@ -94,10 +95,10 @@ def golden_clip_dist():
     import torch.multiprocessing as mp
     out = {}
     port = 29611
-    for world, b, d, scale, seed in ((2, 6, 16, 14.285714, 10), (3, 5, 24, 60.0, 11)):
+    for world, b, d, scale, seed, corr in ((2, 6, 16, 14.285714, 10, 0.5), (3, 5, 24, 60.0, 11, 0.15)):
         ctx = mp.get_context("spawn")
         q = ctx.Queue()
-        procs = [ctx.Process(target=_dist_worker, args=(r, world, port, b, d, scale, seed, q))
+        procs = [ctx.Process(target=_dist_worker, args=(r, world, port, b, d, scale, seed, corr, q))
                  for r in range(world)]
         for p in procs:
             p.start()
@@ -106,7 +107,7 @@ def golden_clip_dist():
             p.join()
         port += 1
         pre = f"w{world}_"
-        I_all, T_all = synth_features(seed, b * world, d)
+        I_all, T_all = synth_features(seed, b * world, d, corr=corr)
         out[pre + "I"] = I_all.numpy()
         out[pre + "T"] = T_all.numpy()
         out[pre + "b"] = np.asarray(b)

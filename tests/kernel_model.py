@@ -1,0 +1,131 @@
+"""Test double for `xtag_clip_b200.kernels.CudaKernels` (TEST INFRASTRUCTURE, lives in tests/ only).
+
+A plain torch fp64 statement of each C entry point's *contract* (include/xtag_b200.h).  Two uses:
+  * CPU tests of the host logic (which collectives, label offsets, gradient weights, slicing) inject it
+    through the `_kernels=` test hook, so world_size-2 gloo tests run without a GPU;
+  * GPU tests compare individual kernel outputs against it.
+It is never importable from the package and never used as a fallback.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+def _f64(t):
+    return t.detach().to(torch.float64)
+
+
+class ModelKernels:
+    name = "model"
+
+    def __init__(self):
+        self.calls = []
+
+    # K3
+    def l2norm_fwd(self, x, out_dtype, eps, want_transposed=False):
+        x64 = _f64(x)
+        n = torch.linalg.vector_norm(x64, dim=-1, keepdim=True).clamp_min(eps)
+        y = (x64 / n).to(out_dtype)
+        inv = (1.0 / n).reshape(-1).to(torch.float32)
+        yT = y.reshape(-1, y.shape[-1]).T.contiguous() if want_transposed else None
+        return y, inv, yT
+
+    def l2norm_bwd(self, gy, y, inv, gx_dtype, eps):
+        g, yy, r = _f64(gy), _f64(y), _f64(inv).reshape(*y.shape[:-1], 1)
+        # the ABI stores inv_norm in fp32: compare in fp32 like the kernel does
+        clamped = inv.reshape(*y.shape[:-1], 1) >= torch.tensor(1.0 / eps, dtype=torch.float32)
+        dot = (g * yy).sum(-1, keepdim=True)
+        gx = torch.where(clamped, g * r, r * (g - yy * dot))
+        return gx.to(gx_dtype)
+
+    # K1
+    def clip_fwd(self, A, Bm, scale, label_offset):
+        self.calls.append(("clip_fwd", tuple(A.shape), tuple(Bm.shape), int(label_offset)))
+        S = float(scale.reshape(-1)[0]) * (_f64(A) @ _f64(Bm).T)
+        M = A.shape[0]
+        idx = torch.arange(M) + label_offset
+        return (torch.logsumexp(S, 1).float(), torch.logsumexp(S, 0).float(), S[torch.arange(M), idx].float())
+
+    def lse_combine(self, parts):
+        return torch.logsumexp(_f64(parts), 0).float()
+
+    def clip_loss(self, row_lse, diag, col_lse, label_offset):
+        M = row_lse.numel()
+        c = _f64(col_lse)[label_offset:label_offset + M]
+        return (0.5 * ((_f64(row_lse) - _f64(diag)).mean() + (c - _f64(diag)).mean())).float()
+
+    # K2
+    def clip_bwd(self, A, Bm, scale, label_offset, row_lse, col_lse, w_row, w_col, w_diag, grad_out,
+                 need_dA, need_dB, grad_dtype):
+        self.calls.append(("clip_bwd", tuple(A.shape), tuple(Bm.shape), int(label_offset), w_row, w_col, w_diag))
+        s = float(scale.reshape(-1)[0])
+        g = float(grad_out.reshape(-1)[0])
+        A64, B64 = _f64(A), _f64(Bm)
+        raw = A64 @ B64.T
+        S = s * raw
+        M, N = S.shape
+        dS = w_row * torch.exp(S - _f64(row_lse)[:, None])
+        if w_col != 0.0:
+            dS = dS + w_col * torch.exp(S - _f64(col_lse)[None, :])
+        eye = torch.zeros(M, N, dtype=torch.float64)
+        eye[torch.arange(M), torch.arange(M) + label_offset] = 1.0
+        dS = g * (dS - w_diag * eye)
+        dA = (s * dS @ B64).to(grad_dtype) if need_dA else None
+        dB = (s * dS.T @ A64).to(grad_dtype) if need_dB else None
+        return dA, dB, (dS * raw).sum().float()
+
+    # K4
+    @staticmethod
+    def _attn(q, k, v, heads, scale):
+        b, Lq, H = q.shape
+        Lk, dh = k.shape[1], H // heads
+        qh = q.reshape(b, Lq, heads, dh).permute(0, 2, 1, 3)
+        kh = k.reshape(b, Lk, heads, dh).permute(0, 2, 1, 3)
+        vh = v.reshape(b, Lk, heads, dh).permute(0, 2, 1, 3)
+        s = qh @ kh.transpose(-1, -2) * scale
+        lse = torch.logsumexp(s, -1)
+        o = (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(b, Lq, H)
+        return o, lse
+
+    def xattn_fwd(self, q, k, v, heads, softmax_scale, dropout_p, seed, offset):
+        assert dropout_p == 0.0, "the contract model covers eval mode"
+        o, lse = self._attn(_f64(q), _f64(k), _f64(v), heads, softmax_scale)
+        return o.to(q.dtype), lse.float()
+
+    def xattn_bwd(self, q, k, v, o, do, lse, heads, softmax_scale, dropout_p, seed, offset):
+        assert dropout_p == 0.0
+        q64, k64, v64 = (_f64(t).requires_grad_(True) for t in (q, k, v))
+        with torch.enable_grad():
+            out, _ = self._attn(q64, k64, v64, heads, softmax_scale)
+            out.backward(_f64(do))
+        return q64.grad.to(q.dtype), k64.grad.to(q.dtype), v64.grad.to(q.dtype)
+
+    # K5
+    def asl(self, x, y, gamma_neg, gamma_pos, clip, eps, want_dx, want_idx):
+        x64 = _f64(x).reshape(-1, x.shape[-1]).requires_grad_(True)
+        y64 = _f64(y).reshape(-1, x.shape[-1])
+        with torch.enable_grad():
+            p = torch.sigmoid(x64)
+            pn = 1 - p
+            if clip and clip > 0:
+                pn = (pn + clip).clamp(max=1)
+            loss = y64 * torch.log(p.clamp(min=eps)) + (1 - y64) * torch.log(pn.clamp(min=eps))
+            if gamma_neg > 0 or gamma_pos > 0:
+                with torch.no_grad():
+                    pt = p * y64 + pn * (1 - y64)
+                    w = torch.pow(1 - pt, gamma_pos * y64 + gamma_neg * (1 - y64))
+                loss = loss * w
+            total = -loss.sum()
+            total.backward()
+        idx = None
+        if want_idx:
+            s = torch.sigmoid(x64.detach())
+            cols, pos = [], 0
+            for size in (3, 4, 3, 4, 4, 4):
+                sc = s[:, pos:pos + size] + s[:, 22 + pos:22 + pos + size]
+                cols.append(sc.argmax(-1, keepdim=True) + pos)
+                pos += size
+            idx = torch.cat(cols, -1).to(torch.int32)
+        return total.detach().float(), (x64.grad.float() if want_dx else None), idx

@@ -1,0 +1,159 @@
+"""CPU tests of the host-side mirror of the reference API (xtag_clip_b200/{loss,tag_head,asymmetric_loss}.py).
+The CUDA kernels are replaced by the contract model in tests/kernel_model.py through the `_kernels=` test hook,
+so what is checked here is the *host logic*: signatures, label offsets, gradient weights, dtype handling,
+state_dict compatibility and error behaviour -- against the golden fixtures produced by the reference."""
+import inspect
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import xtag_clip_b200 as xt
+from oracle.tag_oracle import make_tag_params
+from kernel_model import ModelKernels
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def rel_err(a, b):
+    """max-norm relative error: max|a-b| / max|b| (the measure the parity bars are stated in)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def test_cliploss_signature_matches_reference():
+    sig = inspect.signature(xt.ClipLoss.__init__)
+    names = [p for p in sig.parameters if not p.startswith("_") and p not in ("self", "group", "comm_dtype")]
+    assert names == ["local_loss", "gather_with_grad", "cache_labels", "rank", "world_size", "use_horovod"]
+    defaults = [sig.parameters[n].default for n in names]
+    assert defaults == [False, False, False, 0, 1, False]
+    fsig = inspect.signature(xt.ClipLoss.forward)
+    assert list(fsig.parameters)[1:] == ["image_features", "text_features", "logit_scale", "output_dict"]
+    assert fsig.parameters["output_dict"].default is False
+    gsig = inspect.signature(xt.gather_features)
+    assert list(gsig.parameters) == ["image_features", "text_features", "local_loss", "gather_with_grad", "rank",
+                                     "world_size", "use_horovod"]
+
+
+def test_cliploss_w1_golden(golden_dir):
+    g = _load(golden_dir, "clip_w1.npz")
+    for n in range(int(g["n_cases"])):
+        pre = f"c{n}_f64_"
+        I = torch.from_numpy(g[pre + "I"]).float().requires_grad_(True)
+        T = torch.from_numpy(g[pre + "T"]).float().requires_grad_(True)
+        s = torch.tensor(float(g[pre + "scale"]), requires_grad=True)
+        loss_mod = xt.ClipLoss(_kernels=ModelKernels())
+        out = loss_mod(I, T, s, output_dict=True)
+        assert list(out.keys()) == ["contrastive_loss"]
+        loss = out["contrastive_loss"]
+        assert loss.dim() == 0 and loss.dtype == torch.float32
+        loss.backward()
+        # fp32 inputs/outputs against the reference's fp64 run: the BASELINE "fp32 mode" bar (1e-5)
+        assert rel_err(loss.item(), g[pre + "loss"]) < 1e-5
+        assert rel_err(I.grad.numpy(), g[pre + "dI"]) < 1e-5
+        assert rel_err(T.grad.numpy(), g[pre + "dT"]) < 1e-5
+        assert rel_err(s.grad.numpy(), g[pre + "dscale"]) < 1e-5
+
+
+def test_cliploss_misc_behaviour():
+    k = ModelKernels()
+    I, T = torch.randn(8, 16), torch.randn(8, 16)
+    # python float scale, no grad anywhere
+    l0 = xt.ClipLoss(_kernels=k)(I, T, 7.5)
+    l1 = oracle.clip_loss_single(I.double(), T.double(), torch.tensor(7.5, dtype=torch.float64))
+    np.testing.assert_allclose(l0.item(), l1.item(), rtol=1e-6)
+    # nonscalar_logit_scale: shape [1] scale gets a shape-[1] grad
+    s = torch.tensor([7.5], requires_grad=True)
+    xt.ClipLoss(_kernels=k)(I, T, s).backward()
+    assert s.grad.shape == (1,)
+    # upstream gradient is honoured (GradScaler multiplies the loss)
+    I2 = I.clone().requires_grad_(True)
+    (xt.ClipLoss(_kernels=k)(I2, T, 7.5) * 3.0).backward()
+    I3 = I.clone().requires_grad_(True)
+    xt.ClipLoss(_kernels=k)(I3, T, 7.5).backward()
+    np.testing.assert_allclose(I2.grad.numpy(), 3.0 * I3.grad.numpy(), rtol=1e-5, atol=1e-8)
+    # label cache semantics of get_ground_truth (loss.py:91-102)
+    m = xt.ClipLoss(local_loss=True, cache_labels=True, rank=2, world_size=4)
+    lab = m.get_ground_truth(torch.device("cpu"), 5)
+    assert lab.tolist() == [10, 11, 12, 13, 14] and m.labels[torch.device("cpu")] is lab
+    assert xt.ClipLoss(rank=2, world_size=4).get_ground_truth(torch.device("cpu"), 3).tolist() == [0, 1, 2]
+    # errors
+    with pytest.raises(NotImplementedError):
+        xt.ClipLoss(use_horovod=True)
+    with pytest.raises(ValueError):
+        xt.ClipLoss(_kernels=k)(torch.randn(4, 8), torch.randn(5, 8), 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        xt.ClipLoss()(I, T, 7.5)          # product path on CPU tensors must fail loudly
+
+
+def test_get_logits_slow_path_matches_reference_expression():
+    I, T = torch.randn(6, 8), torch.randn(6, 8)
+    li, lt = xt.ClipLoss().get_logits(I, T, torch.tensor(3.0))
+    ri, rt = oracle.clip_logits(I, T, torch.tensor(3.0))
+    assert torch.equal(li, ri) and torch.equal(lt, rt)
+
+
+def test_create_loss_contract():
+    args = types.SimpleNamespace(distill=False, siglip=False, model="ViT-B-32", local_loss=True,
+                                 gather_with_grad=True, rank=3, world_size=8, horovod=False)
+    m = xt.create_loss(args)
+    assert isinstance(m, xt.ClipLoss)
+    assert (m.local_loss, m.gather_with_grad, m.cache_labels, m.rank, m.world_size) == (True, True, True, 3, 8)
+    args.siglip = True
+    with pytest.raises(NotImplementedError):
+        xt.create_loss(args)
+
+
+def test_l2_normalize_golden(golden_dir):
+    g = _load(golden_dir, "l2norm.npz")
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    y = xt.l2_normalize(x, _kernels=ModelKernels())
+    y.backward(torch.from_numpy(g["gy"]))
+    np.testing.assert_allclose(y.detach().numpy(), g["y"], rtol=1e-11, atol=1e-12)
+    assert rel_err(x.grad.numpy()[[0, 1, 3, 4, 6, 7, 8]], g["gx"][[0, 1, 3, 4, 6, 7, 8]]) < 1e-6   # inv_norm is fp32 in the ABI
+    assert rel_err(x.grad.numpy()[[2, 5]], g["gx"][[2, 5]]) < 1e-6                             # clamped rows: gy / eps
+
+
+def test_asymmetric_loss_golden(golden_dir):
+    g = _load(golden_dir, "asl.npz")
+    for n in range(3):
+        gn, gp, clip = g[f"k{n}_cfg"]
+        x = torch.from_numpy(g["x"]).float().requires_grad_(True)
+        m = xt.AsymmetricLoss(gamma_neg=gn, gamma_pos=gp, clip=clip, _kernels=ModelKernels())
+        loss = m(x, torch.from_numpy(g["y"]).float())
+        loss.backward()
+        np.testing.assert_allclose(loss.item(), g[f"k{n}_loss"], rtol=1e-5)
+        np.testing.assert_allclose(x.grad.numpy(), g[f"k{n}_dx"], rtol=1e-4, atol=1e-6)
+    assert torch.is_grad_enabled()
+    d = inspect.signature(xt.AsymmetricLoss.__init__).parameters
+    assert (d["gamma_neg"].default, d["gamma_pos"].default, d["clip"].default, d["eps"].default) == (4, 1, 0.05, 1e-8)
+
+
+def test_tag_head_golden_and_state_dict(golden_dir):
+    g = _load(golden_dir, "tag_head.npz")
+    for n in range(int(g["n_cases"])):
+        pre = f"t{n}_"
+        seed, D, b, N, gain = g[pre + "cfg"]
+        params = make_tag_params(int(seed), int(D), gain=float(gain), dtype=torch.float64)
+        head = xt.TagHead(int(D), tag_list=list(g[pre + "tag_list"]), _kernels=ModelKernels()).double()
+        assert sorted(head.state_dict().keys()) == list(g[pre + "state_keys"])   # same 35 keys as the reference
+        head.load_state_dict(params, strict=True)
+        head.eval()
+        tokens = torch.from_numpy(g[pre + "tokens"]).requires_grad_(True)
+        logits = head.tag_forward(tokens)
+        assert logits.shape == (int(b), 44)
+        logits.backward(torch.from_numpy(g[pre + "glogits"]))
+        np.testing.assert_allclose(logits.detach().numpy(), g[pre + "logits"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(tokens.grad.numpy(), g[pre + "dtokens"], rtol=1e-8, atol=1e-11)
+        q0 = head.tag_head.encoder.layer[0].crossattention.self.query.weight.grad[:4, :8]
+        k1 = head.tag_head.encoder.layer[1].crossattention.self.key.weight.grad[:4, :8]
+        np.testing.assert_allclose(q0.numpy(), g[pre + "dq0w"], rtol=1e-8, atol=1e-11)
+        np.testing.assert_allclose(k1.numpy(), g[pre + "dk1w"], rtol=1e-8, atol=1e-11)
+        assert head.prepare_control_words(logits.detach()) == list(g[pre + "words"])
+    with pytest.raises(ValueError):
+        head.tag_forward(torch.randn(2, 5, int(D) + 1, dtype=torch.float64))

@@ -1,0 +1,73 @@
+"""ctypes binding of libxtag_b200.so (include/xtag_b200.h).  There is NO fallback: if the
+library is missing or a call fails, a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libxtag_b200.so")
+
+XTAG_F32, XTAG_BF16 = 0, 1
+IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/xtag_b200.h one to one
+SIGNATURES = {
+    "xtag_version": (c_int, []),
+    "xtag_last_error": (c_char_p, []),
+    "xtag_device_check": (c_int, []),
+    "xtag_launch_count": (c_uint64, []),
+    "xtag_l2norm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "xtag_l2norm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                c_void_p]),
+    "xtag_clip_fwd_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "xtag_clip_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "xtag_lse_combine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "xtag_clip_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "xtag_clip_bwd_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "xtag_clip_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                              c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
+                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "xtag_tc_gemm_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "xtag_xattn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                               c_float, c_float, c_uint64, c_uint64, c_void_p]),
+    "xtag_xattn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                               c_void_p, c_void_p, c_void_p,
+                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                               c_float, c_float, c_uint64, c_uint64, c_void_p]),
+    "xtag_asl_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
+                             c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and type the shared library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA library is not built. Run `python -m xtag_clip_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().xtag_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(load().xtag_launch_count())

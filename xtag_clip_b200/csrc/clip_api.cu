@@ -1,0 +1,90 @@
+// C-ABI entry points of the contrastive head: argument validation and SIMT / tcgen05 selection.
+#include "common.cuh"
+
+namespace xtag {
+size_t simt_fwd_ws(int M, int N);
+size_t simt_bwd_ws(int M, int N);
+int simt_clip_fwd(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale, int label_offset,
+                  float* row_lse, float* col_lse, float* diag, void* ws, size_t ws_bytes, cudaStream_t st);
+int simt_clip_bwd(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale, int label_offset,
+                  const float* row_lse, const float* col_lse, float w_row, float w_col, float w_diag,
+                  const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
+                  void* ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_fwd_ws(int M, int N);
+size_t tc_bwd_ws(int M, int N, int D);
+int tc_clip_fwd(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
+                float* row_lse, float* col_lse, float* diag, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
+                const float* row_lse, const float* col_lse, float w_row, float w_col, float w_diag,
+                const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
+                void* ws, size_t ws_bytes, cudaStream_t st);
+
+// tcgen05 path needs bf16 operands whose rows are 16-byte multiples (TMA global stride rule)
+static bool tc_eligible(int dtype, int D) { return dtype == XTAG_BF16 && D % 8 == 0; }
+
+static int resolve_impl(int impl, int dtype, int D, const char* who) {
+  if (impl == XTAG_IMPL_AUTO) return tc_eligible(dtype, D) ? XTAG_IMPL_TC : XTAG_IMPL_SIMT;
+  if (impl == XTAG_IMPL_TC && !tc_eligible(dtype, D)) {
+    set_error("%s: XTAG_IMPL_TC needs bf16 inputs with D %% 8 == 0 (dtype=%d, D=%d)", who, dtype, D);
+    return XTAG_ERR_UNSUPPORTED;
+  }
+  if (impl != XTAG_IMPL_SIMT && impl != XTAG_IMPL_TC) {
+    set_error("%s: unknown impl %d", who, impl);
+    return XTAG_ERR_INVALID;
+  }
+  return impl;
+}
+}  // namespace xtag
+
+using namespace xtag;
+
+extern "C" size_t xtag_clip_fwd_ws_bytes(int M, int N, int D, int dtype, int impl) {
+  if (M <= 0 || N <= 0 || D <= 0) return 0;
+  const int r = resolve_impl(impl, dtype, D, "clip_fwd_ws_bytes");
+  if (r < 0) return 0;
+  return r == XTAG_IMPL_TC ? tc_fwd_ws(M, N) : simt_fwd_ws(M, N);
+}
+
+extern "C" size_t xtag_clip_bwd_ws_bytes(int M, int N, int D, int dtype, int impl) {
+  if (M <= 0 || N <= 0 || D <= 0) return 0;
+  const int r = resolve_impl(impl, dtype, D, "clip_bwd_ws_bytes");
+  if (r < 0) return 0;
+  return r == XTAG_IMPL_TC ? tc_bwd_ws(M, N, D) : simt_bwd_ws(M, N);
+}
+
+extern "C" int xtag_clip_fwd(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale,
+                             int label_offset, float* row_lse, float* col_lse, float* diag, void* ws,
+                             size_t ws_bytes, int impl, void* stream) {
+  XTAG_REQUIRE(A && Bm && scale && row_lse && col_lse && diag, XTAG_ERR_INVALID, "clip_fwd: null pointer");
+  XTAG_REQUIRE(M > 0 && N > 0 && D > 0, XTAG_ERR_INVALID, "clip_fwd: empty problem M=%d N=%d D=%d", M, N, D);
+  XTAG_REQUIRE(dtype == XTAG_F32 || dtype == XTAG_BF16, XTAG_ERR_INVALID, "clip_fwd: bad dtype %d", dtype);
+  XTAG_REQUIRE(label_offset >= 0 && (long)label_offset + M <= (long)N, XTAG_ERR_INVALID,
+               "clip_fwd: labels [%d, %d) fall outside the %d columns", label_offset, label_offset + M, N);
+  int rc = xtag_device_check();
+  if (rc) return rc;
+  const int r = resolve_impl(impl, dtype, D, "clip_fwd");
+  if (r < 0) return r;
+  if (r == XTAG_IMPL_TC)
+    return tc_clip_fwd(A, Bm, M, N, D, scale, label_offset, row_lse, col_lse, diag, ws, ws_bytes, (cudaStream_t)stream);
+  return simt_clip_fwd(A, Bm, dtype, M, N, D, scale, label_offset, row_lse, col_lse, diag, ws, ws_bytes,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int xtag_clip_bwd(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale,
+                             int label_offset, const float* row_lse, const float* col_lse, float w_row, float w_col,
+                             float w_diag, const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
+                             void* ws, size_t ws_bytes, int impl, void* stream) {
+  XTAG_REQUIRE(A && Bm && scale && row_lse && col_lse && grad_out, XTAG_ERR_INVALID, "clip_bwd: null pointer");
+  XTAG_REQUIRE(M > 0 && N > 0 && D > 0, XTAG_ERR_INVALID, "clip_bwd: empty problem M=%d N=%d D=%d", M, N, D);
+  XTAG_REQUIRE((dtype == XTAG_F32 || dtype == XTAG_BF16) && (grad_dtype == XTAG_F32 || grad_dtype == XTAG_BF16),
+               XTAG_ERR_INVALID, "clip_bwd: bad dtype");
+  int rc = xtag_device_check();
+  if (rc) return rc;
+  const int r = resolve_impl(impl, dtype, D, "clip_bwd");
+  if (r < 0) return r;
+  if (r == XTAG_IMPL_TC)
+    return tc_clip_bwd(A, Bm, M, N, D, scale, label_offset, row_lse, col_lse, w_row, w_col, w_diag, grad_out, dA, dB,
+                       grad_dtype, dscale, ws, ws_bytes, (cudaStream_t)stream);
+  return simt_clip_bwd(A, Bm, dtype, M, N, D, scale, label_offset, row_lse, col_lse, w_row, w_col, w_diag, grad_out,
+                       dA, dB, grad_dtype, dscale, ws, ws_bytes, (cudaStream_t)stream);
+}

@@ -1,0 +1,321 @@
+// Contrastive head, fp32 SIMT path ("fp32 mode" of BASELINE.json: parity <= 1e-5) and the small
+// reduction kernels shared with the tcgen05 path.
+//
+// Reference semantics: ClipLoss.get_logits / forward, src/open_clip/loss.py:104-139.
+//   fwd : S = scale * A Bm^T tile by tile (64x64 per CTA, FFMA, fp32 accumulate); per tile the row and
+//         column (max, sum-exp) partials are written as log2-domain LSE partials, S is never stored.
+//   bwd : S tile recomputed, dS staged in fp32, two strided FFMA GEMMs.
+// This path exists for exactness (fp32 inputs, ragged shapes); the bf16 production path is clip_tc.cu.
+#include "common.cuh"
+
+namespace xtag {
+
+constexpr int TS = 64;     // tile edge
+constexpr int TKS = 16;    // k chunk
+
+// C(i,j) = sum_k A[i*sa_m + k*sa_k] * B[j*sb_n + k*sb_k]; 256 threads, 4x4 per thread.
+template <typename TA, typename TB>
+__device__ __forceinline__ void simt_tile_mainloop(float (&acc)[4][4], const TA* __restrict__ A, long sa_m, long sa_k,
+                                                   const TB* __restrict__ B, long sb_n, long sb_k,
+                                                   int M, int N, int K, int m0, int n0,
+                                                   float (*As)[TS + 4], float (*Bs)[TS + 4]) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool a_kfast = (sa_k == 1), b_kfast = (sb_k == 1);
+  for (int k0 = 0; k0 < K; k0 += TKS) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      int r, kk;
+      if (a_kfast) { r = idx >> 4; kk = idx & 15; } else { r = idx & 63; kk = idx >> 6; }
+      const int gi = m0 + r, gk = k0 + kk;
+      As[kk][r] = (gi < M && gk < K) ? to_f32(A[(long)gi * sa_m + (long)gk * sa_k]) : 0.f;
+      if (b_kfast) { r = idx >> 4; kk = idx & 15; } else { r = idx & 63; kk = idx >> 6; }
+      const int gj = n0 + r;
+      const int gk2 = k0 + kk;
+      Bs[kk][r] = (gj < N && gk2 < K) ? to_f32(B[(long)gj * sb_n + (long)gk2 * sb_k]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TKS; ++kk) {
+      float a[4], b[4];
+      *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- forward: LSE partials ----------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) simt_clip_fwd_kernel(const T* __restrict__ A, const T* __restrict__ Bm,
+                                                            int M, int N, int D, const float* __restrict__ scale_p, int label_offset,
+                                                            float* __restrict__ row_part,   // [ntn][M] log2 domain
+                                                            float* __restrict__ col_part,   // [ntm][N] log2 domain
+                                                            float* __restrict__ diag) {     // [M] natural units
+  __shared__ float As[TKS][TS + 4];
+  __shared__ float Bs[TKS][TS + 4];
+  __shared__ float Ts[TS][TS + 1];
+  const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
+  float acc[4][4];
+  simt_tile_mainloop<T, T>(acc, A, D, 1, Bm, D, 1, M, N, D, m0, n0, As, Bs);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float sl2 = scale_p[0] * kLog2e;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Ts[ty * 4 + i][tx * 4 + j] = acc[i][j] * sl2;
+  __syncthreads();
+  const int rows = min(TS, M - m0), cols = min(TS, N - n0);
+  if (tid < TS) {
+    const int r = tid;
+    if (r < rows) {
+      float mx = -INFINITY;
+      for (int c = 0; c < cols; ++c) mx = fmaxf(mx, Ts[r][c]);
+      float l = 0.f;
+      for (int c = 0; c < cols; ++c) l += exp2f(Ts[r][c] - mx);
+      row_part[(size_t)blockIdx.x * M + m0 + r] = mx + log2f(l);
+      const int lab = m0 + r + label_offset;
+      if (lab >= n0 && lab < n0 + cols) diag[m0 + r] = Ts[r][lab - n0] * kLn2;
+    }
+  } else if (tid < 2 * TS) {
+    const int c = tid - TS;
+    if (c < cols) {
+      float mx = -INFINITY;
+      for (int r = 0; r < rows; ++r) mx = fmaxf(mx, Ts[r][c]);
+      float l = 0.f;
+      for (int r = 0; r < rows; ++r) l += exp2f(Ts[r][c] - mx);
+      col_part[(size_t)blockIdx.y * N + n0 + c] = mx + log2f(l);
+    }
+  }
+}
+
+// out[i] = out_mul * log2( sum_p 2^(parts[p*n + i] * in_mul) )        (in_mul/out_mul convert ln <-> log2)
+__global__ void __launch_bounds__(256) lse_reduce_kernel(const float* __restrict__ parts, int P, int n,
+                                                         float in_mul, float out_mul, float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float mx = -INFINITY;
+    for (int p = 0; p < P; ++p) mx = fmaxf(mx, parts[(size_t)p * n + i] * in_mul);
+    float l = 0.f;
+    for (int p = 0; p < P; ++p) l += exp2f(parts[(size_t)p * n + i] * in_mul - mx);
+    out[i] = (mx + log2f(l)) * out_mul;
+  }
+}
+
+int launch_lse_reduce(const float* parts, int P, int n, float in_mul, float out_mul, float* out, cudaStream_t st) {
+  int blocks = (n + 255) / 256;
+  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  if (blocks < 1) blocks = 1;
+  lse_reduce_kernel<<<blocks, 256, 0, st>>>(parts, P, n, in_mul, out_mul, out);
+  XTAG_CHECK_LAUNCH();
+  return XTAG_OK;
+}
+
+// loss = 0.5 * ( mean_i(row_lse_i - diag_i) + mean_i(col_lse[off+i] - diag_i) ); one CTA, fp64 accumulate
+__global__ void __launch_bounds__(1024) clip_loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ diag,
+                                                         const float* __restrict__ col_lse, int M, int label_offset,
+                                                         float* __restrict__ loss_out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x)
+    s += (double)row_lse[i] + (double)col_lse[label_offset + i] - 2.0 * (double)diag[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) loss_out[0] = (float)(0.5 * t / (double)M);
+  }
+}
+
+// ---- backward: dS tile + dscale partial ----------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) simt_clip_ds_kernel(const T* __restrict__ A, const T* __restrict__ Bm,
+                                                           int M, int N, int D, const float* __restrict__ scale_p, int label_offset,
+                                                           const float* __restrict__ row_lse, const float* __restrict__ col_lse,
+                                                           float w_row, float w_col, float w_diag,
+                                                           const float* __restrict__ grad_out,
+                                                           float* __restrict__ dS, float* __restrict__ dscale_part) {
+  __shared__ float As[TKS][TS + 4];
+  __shared__ float Bs[TKS][TS + 4];
+  __shared__ float red[32];
+  const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
+  float acc[4][4];
+  simt_tile_mainloop<T, T>(acc, A, D, 1, Bm, D, 1, M, N, D, m0, n0, As, Bs);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float g = grad_out[0];
+  const float sl2 = scale_p[0] * kLog2e;
+  float part = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = m0 + ty * 4 + i;
+    if (gi >= M) continue;
+    const float rl = row_lse[gi] * kLog2e;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gj = n0 + tx * 4 + j;
+      if (gj >= N) continue;
+      const float v = acc[i][j] * sl2;
+      float d = w_row * exp2f(v - rl) + w_col * exp2f(v - col_lse[gj] * kLog2e);
+      if (gj == gi + label_offset) d -= w_diag;
+      d *= g;
+      dS[(size_t)gi * N + gj] = d;
+      part = fmaf(d, acc[i][j], part);
+    }
+  }
+  part = block_sum(part, red);
+  if (tid == 0) dscale_part[blockIdx.y * gridDim.x + blockIdx.x] = part;
+}
+
+__global__ void __launch_bounds__(1024) sum_into_kernel(const float* __restrict__ parts, int n, float* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)parts[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) out[0] += (float)t;
+  }
+}
+
+int launch_sum_into(const float* parts, int n, float* out, cudaStream_t st) {
+  sum_into_kernel<<<1, 1024, 0, st>>>(parts, n, out);
+  XTAG_CHECK_LAUNCH();
+  return XTAG_OK;
+}
+
+// C[i*ldc + j] = alpha * sum_k A(i,k) B(j,k)   (strided operands, fp32 accumulate)
+template <typename TA, typename TB, typename TC>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const TA* __restrict__ A, long sa_m, long sa_k,
+                                                        const TB* __restrict__ B, long sb_n, long sb_k,
+                                                        TC* __restrict__ C, int ldc, int M, int N, int K, const float* __restrict__ alpha_p) {
+  __shared__ float As[TKS][TS + 4];
+  __shared__ float Bs[TKS][TS + 4];
+  const int m0 = blockIdx.y * TS, n0 = blockIdx.x * TS;
+  float acc[4][4];
+  simt_tile_mainloop<TA, TB>(acc, A, sa_m, sa_k, B, sb_n, sb_k, M, N, K, m0, n0, As, Bs);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float alpha = alpha_p ? alpha_p[0] : 1.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = m0 + ty * 4 + i;
+    if (gi >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gj = n0 + tx * 4 + j;
+      if (gj < N) C[(size_t)gi * ldc + gj] = from_f32<TC>(alpha * acc[i][j]);
+    }
+  }
+}
+
+template <typename T>
+static int simt_fwd(const T* A, const T* Bm, int M, int N, int D, const float* scale, int label_offset,
+                    float* row_lse, float* col_lse, float* diag, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int ntm = (M + TS - 1) / TS, ntn = (N + TS - 1) / TS;
+  const size_t need = ((size_t)ntn * M + (size_t)ntm * N) * sizeof(float);
+  XTAG_REQUIRE(ws && ws_bytes >= need, XTAG_ERR_WORKSPACE, "clip_fwd(simt): workspace %zu < %zu", ws_bytes, need);
+  float* row_part = (float*)ws;
+  float* col_part = row_part + (size_t)ntn * M;
+  simt_clip_fwd_kernel<T><<<dim3(ntn, ntm), 256, 0, st>>>(A, Bm, M, N, D, scale, label_offset, row_part, col_part, diag);
+  XTAG_CHECK_LAUNCH();
+  int rc = launch_lse_reduce(row_part, ntn, M, 1.f, kLn2, row_lse, st);
+  if (rc) return rc;
+  return launch_lse_reduce(col_part, ntm, N, 1.f, kLn2, col_lse, st);
+}
+
+size_t simt_fwd_ws(int M, int N) {
+  const size_t ntm = (M + TS - 1) / TS, ntn = (N + TS - 1) / TS;
+  return (ntn * (size_t)M + ntm * (size_t)N) * sizeof(float) + 256;
+}
+size_t simt_bwd_ws(int M, int N) {
+  const size_t ntm = (M + TS - 1) / TS, ntn = (N + TS - 1) / TS;
+  return ((size_t)M * N + ntm * ntn) * sizeof(float) + 256;
+}
+
+int simt_clip_fwd(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale, int label_offset,
+                  float* row_lse, float* col_lse, float* diag, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (dtype == XTAG_F32)
+    return simt_fwd<float>((const float*)A, (const float*)Bm, M, N, D, scale, label_offset, row_lse, col_lse, diag, ws, ws_bytes, st);
+  return simt_fwd<__nv_bfloat16>((const __nv_bfloat16*)A, (const __nv_bfloat16*)Bm, M, N, D, scale, label_offset,
+                                 row_lse, col_lse, diag, ws, ws_bytes, st);
+}
+
+template <typename T, typename TG>
+static int simt_bwd(const T* A, const T* Bm, int M, int N, int D, const float* scale, int label_offset,
+                    const float* row_lse, const float* col_lse, float w_row, float w_col, float w_diag,
+                    const float* grad_out, TG* dA, TG* dB, float* dscale, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int ntm = (M + TS - 1) / TS, ntn = (N + TS - 1) / TS;
+  const size_t need = ((size_t)M * N + (size_t)ntm * ntn) * sizeof(float);
+  XTAG_REQUIRE(ws && ws_bytes >= need, XTAG_ERR_WORKSPACE, "clip_bwd(simt): workspace %zu < %zu", ws_bytes, need);
+  float* dS = (float*)ws;
+  float* part = dS + (size_t)M * N;
+  simt_clip_ds_kernel<T><<<dim3(ntn, ntm), 256, 0, st>>>(A, Bm, M, N, D, scale, label_offset, row_lse, col_lse,
+                                                          w_row, w_col, w_diag, grad_out, dS, part);
+  XTAG_CHECK_LAUNCH();
+  if (dscale) {
+    int rc = launch_sum_into(part, ntm * ntn, dscale, st);
+    if (rc) return rc;
+  }
+  const int ntd = (D + TS - 1) / TS;
+  if (dA) {   // dA[i,d] = scale * sum_j dS[i,j] Bm[j,d]
+    simt_gemm_kernel<float, T, TG><<<dim3(ntd, ntm), 256, 0, st>>>(dS, N, 1, Bm, 1, D, dA, D, M, D, N, scale);
+    XTAG_CHECK_LAUNCH();
+  }
+  if (dB) {   // dB[j,d] = scale * sum_i dS[i,j] A[i,d]
+    simt_gemm_kernel<float, T, TG><<<dim3(ntd, ntn), 256, 0, st>>>(dS, 1, N, A, 1, D, dB, D, N, D, M, scale);
+    XTAG_CHECK_LAUNCH();
+  }
+  return XTAG_OK;
+}
+
+int simt_clip_bwd(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale, int label_offset,
+                  const float* row_lse, const float* col_lse, float w_row, float w_col, float w_diag,
+                  const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
+  typedef __nv_bfloat16 bf16;
+  if (dtype == XTAG_F32 && grad_dtype == XTAG_F32)
+    return simt_bwd<float, float>((const float*)A, (const float*)Bm, M, N, D, scale, label_offset, row_lse, col_lse,
+                                  w_row, w_col, w_diag, grad_out, (float*)dA, (float*)dB, dscale, ws, ws_bytes, st);
+  if (dtype == XTAG_BF16 && grad_dtype == XTAG_F32)
+    return simt_bwd<bf16, float>((const bf16*)A, (const bf16*)Bm, M, N, D, scale, label_offset, row_lse, col_lse,
+                                 w_row, w_col, w_diag, grad_out, (float*)dA, (float*)dB, dscale, ws, ws_bytes, st);
+  if (dtype == XTAG_BF16 && grad_dtype == XTAG_BF16)
+    return simt_bwd<bf16, bf16>((const bf16*)A, (const bf16*)Bm, M, N, D, scale, label_offset, row_lse, col_lse,
+                                w_row, w_col, w_diag, grad_out, (bf16*)dA, (bf16*)dB, dscale, ws, ws_bytes, st);
+  return simt_bwd<float, bf16>((const float*)A, (const float*)Bm, M, N, D, scale, label_offset, row_lse, col_lse,
+                               w_row, w_col, w_diag, grad_out, (bf16*)dA, (bf16*)dB, dscale, ws, ws_bytes, st);
+}
+
+}  // namespace xtag
+
+using namespace xtag;
+
+extern "C" int xtag_lse_combine(const float* parts, int W, int N, float* out, void* stream) {
+  XTAG_REQUIRE(parts && out && W > 0 && N >= 0, XTAG_ERR_INVALID, "lse_combine: bad arguments");
+  if (N == 0) return XTAG_OK;
+  return launch_lse_reduce(parts, W, N, kLog2e, kLn2, out, (cudaStream_t)stream);
+}
+
+extern "C" int xtag_clip_loss(const float* row_lse, const float* diag, const float* col_lse, int M, int label_offset,
+                              float* loss_out, void* stream) {
+  XTAG_REQUIRE(row_lse && diag && col_lse && loss_out && M > 0 && label_offset >= 0, XTAG_ERR_INVALID,
+               "clip_loss: bad arguments");
+  clip_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_lse, diag, col_lse, M, label_offset, loss_out);
+  XTAG_CHECK_LAUNCH();
+  return XTAG_OK;
+}

@@ -1,0 +1,622 @@
+// Contrastive head, bf16 production path: tcgen05 / TMEM / TMA (sm_100a).
+//
+// One persistent, warp-specialised kernel template computes  acc[M,N] = A[M,K] * B[N,K]^T  (both operands
+// bf16, K-major, fp32 accumulation in TMEM) over 128x256 tiles and hands every finished accumulator to one
+// of three fused epilogues:
+//
+//   EPI_LSE    K1 forward   S = scale*acc never leaves the SM: per tile the epilogue emits log2-domain
+//                           (max,sum-exp) partials per row and per column and picks the label logit
+//                           (reference src/open_clip/loss.py:116-124 + F.cross_entropy at :134-137)
+//   EPI_DS     K2 backward  S recomputed, dS = g*(w_row*softmax_row + w_col*softmax_col - w_diag*1[label])
+//                           written once as bf16 in both orientations (dS and dS^T) + d(logit_scale) partials
+//   EPI_STORE  plain GEMM   C = alpha*acc (fp32 or bf16): dA = scale*dS*Bm and dB = scale*dS^T*A
+//
+// Pipeline per CTA (384 threads, 1 CTA / SM, grid = #SMs, static tile schedule with grouped rasterisation):
+//   warp 0      TMA producer  : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a 4-stage smem ring
+//   warp 1      MMA issuer    : one elected lane issues tcgen05.mma 128x256x16, commits to mbarriers
+//   warp 2      TMEM allocator: 512 columns = two 128x256 fp32 accumulators (epilogue of tile i overlaps
+//                               the MMAs of tile i+1)
+//   warps 4-11  epilogue      : tcgen05.ld 32x32b (lane = row), 2 warps per TMEM lane quadrant, each owning
+//                               one 128-column half of the accumulator
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace xtag {
+
+using namespace ptx;
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int kStages = 4;
+constexpr int kABytes = BM * BK * 2;          // 16 KB
+constexpr int kBBytes = BN * BK * 2;          // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + 32 * kEpiWarps;   // 384
+constexpr int kTmemCols = 512;
+constexpr int kGroupM = 16;
+constexpr int kEpiScratchFloats = 2 /*acc*/ * 2 /*half*/ * 4 /*quadrant*/ * 128;   // 8 KB
+constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 256 /*barriers*/ + kEpiScratchFloats * 4;
+
+enum { EPI_LSE = 0, EPI_DS = 1, EPI_STORE = 2 };
+
+struct EpiParams {
+  // EPI_LSE
+  const float* scale_p;   // device scalar: logit scale (natural units)
+  int label_offset;
+  float* row_part;        // [2*num_n][M]   log2-domain LSE partial per (n tile, column half)
+  float* col_part;        // [num_m][N]     log2-domain LSE partial per m tile
+  float* diag;            // [M]            natural units
+  // EPI_DS
+  const float* row_lse;   // [M] natural
+  const float* col_lse;   // [N] natural
+  float w_row, w_col, w_diag;
+  const float* grad_out;  // device scalar
+  __nv_bfloat16* dS;      // [M][ldds]
+  __nv_bfloat16* dST;     // [N][lddst]   (may be null)
+  int ldds, lddst;
+  float* dscale_part;     // [grid * kEpiWarps]
+  // EPI_STORE
+  void* C;
+  int ldc;
+  int c_is_bf16;
+  float alpha;            // C = alpha * (alpha_p ? *alpha_p : 1) * acc
+  const float* alpha_p;
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
+  const int per_group = kGroupM * num_n;
+  const int group = tile / per_group;
+  const int first_m = group * kGroupM;
+  const int gsize = min(num_m - first_m, kGroupM);
+  const int in = tile - group * per_group;
+  m_blk = first_m + in % gsize;
+  n_blk = in / gsize;
+}
+
+// Transpose-reduce over the 32 lanes of a warp: on entry x[j] is lane-local value for column j; on exit
+// x[0] on lane L holds op-reduction over all lanes of column L.  31 shuffles.
+template <bool kMax>
+__device__ __forceinline__ void warp_transpose_reduce(float (&x)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int t = 0; t < o; ++t) {
+      const float send = upper ? x[t] : x[t + o];
+      const float keep = upper ? x[t + o] : x[t];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, o);
+      x[t] = kMax ? fmaxf(keep, recv) : (keep + recv);
+    }
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               int M, int N, int K, EpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full_bar = bars;                      // [kStages]
+  uint64_t* empty_bar = bars + kStages;           // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;       // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* epi_scratch = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + BK - 1) / BK;
+
+  if (warp == 0 && elect_one()) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull_bar[i]), 1);
+      mbar_init(smem_u32(&tempty_bar[i]), kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(tile, num_m, num_n, m_blk, n_blk);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(fb, kStageBytes);
+          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+          tma_load_2d(sa, &tmA, fb, kb * BK, m_blk * BM);
+          tma_load_2d(sa + kABytes, &tmB, fb, kb * BK, n_blk * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN, 0, 0);
+      constexpr uint64_t desc_hi = make_smem_desc_hi(16, 1024, kSwizzle128B);   // K-major, 128B swizzle
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
+          const uint64_t da = make_smem_desc(sa, desc_hi);
+          const uint64_t db = make_smem_desc(sa + kABytes, desc_hi);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes per 16-element K step inside the 128-byte swizzle row (encoded >> 4)
+            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));       // frees the smem slot when the MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tfull_bar[acc]));           // accumulator ready for the epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue =========================================
+    const int e = warp - 4;
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int h = e >> 2;              // which 128-column half of the accumulator
+    const int bar_id = 1 + h;          // named barrier shared by the 4 warps of one half
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float dscale_acc = 0.f;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(tile, num_m, num_n, m_blk, n_blk);
+      const int gi = m_blk * BM + q * 32 + lane;          // this thread's row
+      const int n_base = n_blk * BN + h * 128;            // first column of this warp's half
+      const bool row_ok = gi < M;
+      float* scratch = epi_scratch + ((acc * 2 + h) * 4) * 128;   // [4][128] for this (acc, half)
+
+      if constexpr (EPI == EPI_DS) {
+        // stage log2-domain column LSEs of this half in smem before touching TMEM
+        const int c = q * 32 + lane;
+        const int gj = n_base + c;
+        scratch[c] = (gj < N) ? ep.col_lse[gj] * kLog2e : 0.f;
+        named_bar_sync(bar_id, 128);
+      }
+
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + h * 128);
+
+      if constexpr (EPI == EPI_LSE) {
+        const float sl2 = ep.scale_p[0] * kLog2e;
+        float m_run = -INFINITY, l_run = 0.f;
+        const int lab = gi + ep.label_offset;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          const int c0 = n_base + ch * 32;
+          float v[32], x[32];
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool col_ok = (c0 + j) < N;
+            const float s = __uint_as_float(r[j]) * sl2;
+            v[j] = col_ok ? s : -INFINITY;
+            cm = fmaxf(cm, v[j]);
+            x[j] = row_ok ? v[j] : -INFINITY;
+          }
+          // ---- row statistics (thread local, online) ----
+          if (cm > -INFINITY) {
+            const float m_new = fmaxf(m_run, cm);
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += fast_exp2(v[j] - m_new);
+            l_run = l_run * fast_exp2(m_run - m_new) + sum;
+            m_run = m_new;
+          }
+          if (row_ok && lab >= c0 && lab < c0 + 32) {
+            float dv = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dv = (lab - c0 == j) ? v[j] : dv;
+            ep.diag[gi] = dv * kLn2;
+          }
+          // ---- column statistics over this warp's 32 rows (exact: per-column max, then sum) ----
+          warp_transpose_reduce<true>(x, lane);                 // x[0] = max of column `lane`
+          float* cmax_s = scratch + q * 128 + ch * 32;          // reuse the output slot as staging
+          cmax_s[lane] = x[0];
+          __syncwarp();
+          float ex[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cmax_s + j4 * 4);
+            const float cmx[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j4 * 4 + u;
+              // column with no valid entry: max = -inf -> contributes nothing
+              ex[j] = (row_ok && cmx[u] > -INFINITY) ? fast_exp2(v[j] - cmx[u]) : 0.f;
+            }
+          }
+          __syncwarp();
+          const float my_cmax = x[0];
+          warp_transpose_reduce<false>(ex, lane);               // ex[0] = sum of column `lane`
+          cmax_s[lane] = (ex[0] > 0.f) ? my_cmax + fast_log2(ex[0]) : -INFINITY;
+        }
+        // row partial for this (n tile, half)
+        if (row_ok)
+          ep.row_part[(size_t)(n_blk * 2 + h) * M + gi] = (l_run > 0.f) ? m_run + fast_log2(l_run) : -INFINITY;
+        // TMEM reads of this warp are complete: release the accumulator early
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        // combine the four quadrant partials of each column
+        named_bar_sync(bar_id, 128);
+        {
+          const int c = q * 32 + lane;
+          const float p0 = scratch[0 * 128 + c], p1 = scratch[1 * 128 + c];
+          const float p2 = scratch[2 * 128 + c], p3 = scratch[3 * 128 + c];
+          const float mx = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
+          float out = -INFINITY;
+          if (mx > -INFINITY)
+            out = mx + fast_log2(fast_exp2(p0 - mx) + fast_exp2(p1 - mx) + fast_exp2(p2 - mx) + fast_exp2(p3 - mx));
+          const int gj = n_base + c;
+          if (gj < N) ep.col_part[(size_t)m_blk * N + gj] = out;
+        }
+      } else if constexpr (EPI == EPI_DS) {
+        const float sl2 = ep.scale_p[0] * kLog2e;
+        const float g = ep.grad_out[0];
+        const float wr = ep.w_row * g, wc = ep.w_col * g, wd = ep.w_diag * g;
+        const float rl2 = row_ok ? ep.row_lse[gi] * kLog2e : 0.f;
+        const int lab = gi + ep.label_offset;
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          const int c0 = n_base + ch * 32;
+          float d[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(scratch + ch * 32 + j4 * 4);
+            const float cl2[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j4 * 4 + u;
+              const float a = __uint_as_float(r[j]);
+              const float v = a * sl2;
+              float dd = wr * fast_exp2(v - rl2) + wc * fast_exp2(v - cl2[u]);
+              dd = (lab == c0 + j) ? dd - wd : dd;
+              dd = (row_ok && (c0 + j) < N) ? dd : 0.f;
+              d[j] = dd;
+              dscale_acc = fmaf(dd, a, dscale_acc);
+            }
+          }
+          if (row_ok) {
+            __nv_bfloat16* dst = ep.dS + (size_t)gi * ep.ldds + c0;
+            if (c0 + 32 <= N) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                uint4 pk;
+                __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) hp[u] = __floats2bfloat162_rn(d[j8 * 8 + 2 * u], d[j8 * 8 + 2 * u + 1]);
+                *reinterpret_cast<uint4*>(dst + j8 * 8) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < N) dst[j] = __float2bfloat16_rn(d[j]);
+            }
+          }
+          if (ep.dST != nullptr && row_ok) {
+            // transposed copy: for a fixed column the warp writes 32 consecutive rows (64 B)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < N) ep.dST[(size_t)(c0 + j) * ep.lddst + gi] = __float2bfloat16_rn(d[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      } else {
+        // ---------------- EPI_STORE ----------------
+        const float alpha = ep.alpha * (ep.alpha_p ? ep.alpha_p[0] : 1.f);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          const int c0 = n_base + ch * 32;
+          if (row_ok) {
+            if (ep.c_is_bf16) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.C) + (size_t)gi * ep.ldc + c0;
+              if (c0 + 32 <= N && (ep.ldc % 8) == 0) {
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                  uint4 pk;
+                  __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                    hp[u] = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 2 * u]) * alpha,
+                                                  __uint_as_float(r[j8 * 8 + 2 * u + 1]) * alpha);
+                  *reinterpret_cast<uint4*>(dst + j8 * 8) = pk;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c0 + j < N) dst[j] = __float2bfloat16_rn(__uint_as_float(r[j]) * alpha);
+              }
+            } else {
+              float* dst = reinterpret_cast<float*>(ep.C) + (size_t)gi * ep.ldc + c0;
+              if (c0 + 32 <= N && (ep.ldc % 4) == 0) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                  *reinterpret_cast<float4*>(dst + j4 * 4) =
+                      make_float4(__uint_as_float(r[j4 * 4]) * alpha, __uint_as_float(r[j4 * 4 + 1]) * alpha,
+                                  __uint_as_float(r[j4 * 4 + 2]) * alpha, __uint_as_float(r[j4 * 4 + 3]) * alpha);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (c0 + j < N) dst[j] = __uint_as_float(r[j]) * alpha;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if constexpr (EPI == EPI_DS) {
+      dscale_acc = warp_sum(dscale_acc);
+      if (lane == 0) ep.dscale_part[blockIdx.x * kEpiWarps + e] = dscale_acc;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] matrix with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle
+static int make_tmap_bf16(CUtensorMap* tm, const void* base, int rows, int cols, long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  XTAG_REQUIRE(enc != nullptr, XTAG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  XTAG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, XTAG_ERR_UNSUPPORTED,
+               "TMA operand must be 16-byte aligned with a 16-byte multiple row stride (ld=%ld)", ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XTAG_REQUIRE(r == CUDA_SUCCESS, XTAG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return XTAG_OK;
+}
+
+template <int EPI>
+static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiParams& ep,
+                     cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, B, N, K, ldb, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XTAG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int grid = num_sms();
+  if (grid > num_tiles) grid = num_tiles;
+  tc_gemm_kernel<EPI><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, M, N, K, ep);
+  XTAG_CHECK_LAUNCH();
+  return XTAG_OK;
+}
+
+int tc_grid_for(int M, int N) {
+  const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int grid = num_sms();
+  return grid > num_tiles ? num_tiles : grid;
+}
+
+int launch_lse_reduce(const float* parts, int P, int n, float in_mul, float out_mul, float* out, cudaStream_t st);
+int launch_sum_into(const float* parts, int n, float* out, cudaStream_t st);
+int launch_transpose(const void* in, void* out, int dtype, int rows, int cols, cudaStream_t st);
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t tc_fwd_ws(int M, int N) {
+  const size_t num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  return align256(2 * num_n * (size_t)M * 4) + align256(num_m * (size_t)N * 4) + 256;
+}
+
+int tc_clip_fwd(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
+                float* row_lse, float* col_lse, float* diag, void* ws, size_t ws_bytes, cudaStream_t st) {
+  XTAG_REQUIRE(ws && ws_bytes >= tc_fwd_ws(M, N), XTAG_ERR_WORKSPACE, "clip_fwd(tc): workspace %zu < %zu", ws_bytes,
+               tc_fwd_ws(M, N));
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  EpiParams ep = {};
+  ep.scale_p = scale;
+  ep.label_offset = label_offset;
+  ep.row_part = (float*)ws;
+  ep.col_part = (float*)((uint8_t*)ws + align256(2 * (size_t)num_n * M * 4));
+  ep.diag = diag;
+  int rc = launch_tc<EPI_LSE>(A, D, Bm, D, M, N, D, ep, st);
+  if (rc) return rc;
+  rc = launch_lse_reduce(ep.row_part, 2 * num_n, M, 1.f, kLn2, row_lse, st);
+  if (rc) return rc;
+  return launch_lse_reduce(ep.col_part, num_m, N, 1.f, kLn2, col_lse, st);
+}
+
+// workspace: dS [M][Np] bf16, dS^T [N][Mp] bf16, A^T [D][Mp] bf16, Bm^T [D][Np] bf16, dscale partials
+struct BwdLayout {
+  size_t Mp, Np, off_ds, off_dst, off_at, off_bt, off_part, total;
+};
+static BwdLayout bwd_layout(int M, int N, int D) {
+  BwdLayout L;
+  L.Mp = ((size_t)M + 7) & ~(size_t)7;
+  L.Np = ((size_t)N + 7) & ~(size_t)7;
+  size_t o = 0;
+  L.off_ds = o;   o += align256((size_t)M * L.Np * 2);
+  L.off_dst = o;  o += align256((size_t)N * L.Mp * 2);
+  L.off_at = o;   o += align256((size_t)D * L.Mp * 2);
+  L.off_bt = o;   o += align256((size_t)D * L.Np * 2);
+  L.off_part = o; o += align256((size_t)256 * kEpiWarps * 4);
+  L.total = o + 256;
+  return L;
+}
+size_t tc_bwd_ws(int M, int N, int D) { return bwd_layout(M, N, D).total; }
+
+__global__ void __launch_bounds__(256) transpose_pad_bf16_kernel(const __nv_bfloat16* __restrict__ in,
+                                                                 __nv_bfloat16* __restrict__ out, int rows, int cols,
+                                                                 int ld_out) {
+  // out[c][r] = in[r][c]; out rows padded to ld_out (pad columns zeroed)
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i, c = c0 + tx;
+    tile[ty + i][tx] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, r = r0 + tx;
+    if (c < cols && r < ld_out) out[(size_t)c * ld_out + r] = tile[tx][ty + i];
+  }
+}
+
+int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
+                const float* row_lse, const float* col_lse, float w_row, float w_col, float w_diag,
+                const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
+                void* ws, size_t ws_bytes, cudaStream_t st) {
+  const BwdLayout L = bwd_layout(M, N, D);
+  XTAG_REQUIRE(ws && ws_bytes >= L.total, XTAG_ERR_WORKSPACE, "clip_bwd(tc): workspace %zu < %zu", ws_bytes, L.total);
+  uint8_t* w = (uint8_t*)ws;
+  __nv_bfloat16* dS = (__nv_bfloat16*)(w + L.off_ds);
+  __nv_bfloat16* dST = (__nv_bfloat16*)(w + L.off_dst);
+  __nv_bfloat16* At = (__nv_bfloat16*)(w + L.off_at);
+  __nv_bfloat16* Bt = (__nv_bfloat16*)(w + L.off_bt);
+  float* part = (float*)(w + L.off_part);
+
+  // padding columns of dS / dS^T must be zero when M or N is not a multiple of 8 (they enter the K sums)
+  if (L.Np != (size_t)N) XTAG_CUDA(cudaMemsetAsync(dS, 0, (size_t)M * L.Np * 2, st));
+  if (dB && L.Mp != (size_t)M) XTAG_CUDA(cudaMemsetAsync(dST, 0, (size_t)N * L.Mp * 2, st));
+
+  EpiParams ep = {};
+  ep.scale_p = scale;
+  ep.label_offset = label_offset;
+  ep.row_lse = row_lse;
+  ep.col_lse = col_lse;
+  ep.w_row = w_row; ep.w_col = w_col; ep.w_diag = w_diag;
+  ep.grad_out = grad_out;
+  ep.dS = dS; ep.ldds = (int)L.Np;
+  ep.dST = dB ? dST : nullptr; ep.lddst = (int)L.Mp;
+  ep.dscale_part = part;
+  const int grid = tc_grid_for(M, N);
+  int rc = launch_tc<EPI_DS>(A, D, Bm, D, M, N, D, ep, st);
+  if (rc) return rc;
+  if (dscale) {
+    rc = launch_sum_into(part, grid * kEpiWarps, dscale, st);
+    if (rc) return rc;
+  }
+  if (dA) {
+    // dA[M,D] = scale * dS[M,N] * Bm[N,D]  ==  dS (K-major over j)  x  (Bm^T)[D,N] (K-major over j)
+    dim3 g((D + 31) / 32, (N + 31) / 32);
+    transpose_pad_bf16_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)Bm, Bt, N, D, (int)L.Np);
+    XTAG_CHECK_LAUNCH();
+    EpiParams es = {};
+    es.C = dA; es.ldc = D; es.c_is_bf16 = (grad_dtype == XTAG_BF16); es.alpha = 1.f; es.alpha_p = scale;
+    rc = launch_tc<EPI_STORE>(dS, (long)L.Np, Bt, (long)L.Np, M, D, N, es, st);
+    if (rc) return rc;
+  }
+  if (dB) {
+    // dB[N,D] = scale * dS^T[N,M] * A[M,D]  ==  dS^T (K-major over i)  x  (A^T)[D,M] (K-major over i)
+    dim3 g((D + 31) / 32, (M + 31) / 32);
+    transpose_pad_bf16_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)A, At, M, D, (int)L.Mp);
+    XTAG_CHECK_LAUNCH();
+    EpiParams es = {};
+    es.C = dB; es.ldc = D; es.c_is_bf16 = (grad_dtype == XTAG_BF16); es.alpha = 1.f; es.alpha_p = scale;
+    rc = launch_tc<EPI_STORE>(dST, (long)L.Mp, At, (long)L.Mp, N, D, M, es, st);
+    if (rc) return rc;
+  }
+  return XTAG_OK;
+}
+
+}  // namespace xtag
+
+using namespace xtag;
+
+extern "C" int xtag_tc_gemm_nt(const void* A, const void* B, void* C, int c_dtype, int M, int N, int K, float alpha,
+                               void* stream) {
+  XTAG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, XTAG_ERR_INVALID, "tc_gemm_nt: bad arguments");
+  XTAG_REQUIRE(K % 8 == 0, XTAG_ERR_UNSUPPORTED, "tc_gemm_nt: K must be a multiple of 8 (16-byte TMA rows)");
+  XTAG_REQUIRE(c_dtype == XTAG_F32 || c_dtype == XTAG_BF16, XTAG_ERR_INVALID, "tc_gemm_nt: bad C dtype");
+  int rc = xtag_device_check();
+  if (rc) return rc;
+  EpiParams es = {};
+  es.C = C; es.ldc = N; es.c_is_bf16 = (c_dtype == XTAG_BF16); es.alpha = alpha; es.alpha_p = nullptr;
+  return launch_tc<EPI_STORE>(A, K, B, K, M, N, K, es, (cudaStream_t)stream);
+}

@@ -1,0 +1,202 @@
+"""Tensor-level wrappers over the C ABI (include/xtag_b200.h).
+
+`CudaKernels` is the only kernel provider the product code uses.  It passes raw device
+pointers of torch tensors and the current CUDA stream to libxtag_b200.so; torch is used for
+allocation and stream plumbing only.  Every method raises if its inputs are not CUDA tensors:
+there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import XTAG_BF16, XTAG_F32, IMPL_AUTO, check
+
+_DT = {torch.float32: XTAG_F32, torch.bfloat16: XTAG_BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"xtag kernels take float32 or bfloat16 tensors, got {t.dtype}") from None
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("xtag_clip_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback "
+                               f"(got a tensor on {t.device})")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class CudaKernels:
+    """One method per C entry point.  Shapes/semantics: see include/xtag_b200.h."""
+
+    name = "cuda"
+
+    def __init__(self, impl: int = IMPL_AUTO):
+        self.lib = _lib.load()
+        self.impl = impl
+
+    # ---- K3 ----------------------------------------------------------------------------------
+    def l2norm_fwd(self, x: torch.Tensor, out_dtype: torch.dtype, eps: float, want_transposed: bool = False):
+        _cuda(x)
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        rows, dim = x2.shape
+        y = torch.empty((rows, dim), dtype=out_dtype, device=x.device)
+        yT = torch.empty((dim, rows), dtype=out_dtype, device=x.device) if want_transposed else None
+        inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        if rows:
+            check(self.lib.xtag_l2norm_fwd(_p(x2), _dt(x2), _p(y), _DT[out_dtype], _p(yT), _p(inv), rows, dim,
+                                           float(eps), _stream()), "xtag_l2norm_fwd")
+        return y.reshape(x.shape), inv, yT
+
+    def l2norm_bwd(self, gy: torch.Tensor, y: torch.Tensor, inv: torch.Tensor, gx_dtype: torch.dtype, eps: float):
+        _cuda(gy, y, inv)
+        y2 = y.reshape(-1, y.shape[-1]).contiguous()
+        g2 = gy.reshape(-1, y.shape[-1]).to(y2.dtype).contiguous()
+        rows, dim = y2.shape
+        gx = torch.empty((rows, dim), dtype=gx_dtype, device=y.device)
+        if rows:
+            check(self.lib.xtag_l2norm_bwd(_p(g2), _dt(g2), _p(y2), _dt(y2), _p(inv), _p(gx), _DT[gx_dtype], rows, dim,
+                                           float(eps), _stream()), "xtag_l2norm_bwd")
+        return gx.reshape(y.shape)
+
+    # ---- K1 ----------------------------------------------------------------------------------
+    def clip_fwd(self, A: torch.Tensor, Bm: torch.Tensor, scale: torch.Tensor, label_offset: int
+                 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """-> (row_lse [M], col_lse_partial [N], diag [M]), fp32, natural-log units."""
+        _cuda(A, Bm, scale)
+        assert A.dtype == Bm.dtype and A.dim() == 2 and Bm.dim() == 2 and A.shape[1] == Bm.shape[1]
+        A, Bm = A.contiguous(), Bm.contiguous()
+        M, D = A.shape
+        N = Bm.shape[0]
+        dev = A.device
+        row_lse = torch.empty(M, dtype=torch.float32, device=dev)
+        col_lse = torch.empty(N, dtype=torch.float32, device=dev)
+        diag = torch.empty(M, dtype=torch.float32, device=dev)
+        nbytes = int(self.lib.xtag_clip_fwd_ws_bytes(M, N, D, _dt(A), self.impl))
+        if nbytes == 0:
+            check(-1, "xtag_clip_fwd_ws_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(self.lib.xtag_clip_fwd(_p(A), _p(Bm), _dt(A), M, N, D, _p(scale), int(label_offset),
+                                     _p(row_lse), _p(col_lse), _p(diag), _p(ws), nbytes, self.impl, _stream()),
+              "xtag_clip_fwd")
+        return row_lse, col_lse, diag
+
+    def lse_combine(self, parts: torch.Tensor) -> torch.Tensor:
+        _cuda(parts)
+        parts = parts.contiguous()
+        W, N = parts.shape
+        out = torch.empty(N, dtype=torch.float32, device=parts.device)
+        check(self.lib.xtag_lse_combine(_p(parts), W, N, _p(out), _stream()), "xtag_lse_combine")
+        return out
+
+    def clip_loss(self, row_lse: torch.Tensor, diag: torch.Tensor, col_lse: torch.Tensor, label_offset: int):
+        _cuda(row_lse, diag, col_lse)
+        out = torch.empty((), dtype=torch.float32, device=row_lse.device)
+        check(self.lib.xtag_clip_loss(_p(row_lse), _p(diag), _p(col_lse), row_lse.numel(), int(label_offset),
+                                      _p(out), _stream()), "xtag_clip_loss")
+        return out
+
+    # ---- K2 ----------------------------------------------------------------------------------
+    def clip_bwd(self, A, Bm, scale, label_offset, row_lse, col_lse, w_row, w_col, w_diag, grad_out,
+                 need_dA: bool, need_dB: bool, grad_dtype: torch.dtype):
+        """-> (dA [M,D] | None, dB [N,D] | None, dscale 0-d fp32)"""
+        _cuda(A, Bm, scale, row_lse, col_lse, grad_out)
+        A, Bm = A.contiguous(), Bm.contiguous()
+        M, D = A.shape
+        N = Bm.shape[0]
+        dev = A.device
+        dA = torch.empty((M, D), dtype=grad_dtype, device=dev) if need_dA else None
+        dB = torch.empty((N, D), dtype=grad_dtype, device=dev) if need_dB else None
+        dscale = torch.zeros((), dtype=torch.float32, device=dev)
+        g = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        nbytes = int(self.lib.xtag_clip_bwd_ws_bytes(M, N, D, _dt(A), self.impl))
+        if nbytes == 0:
+            check(-1, "xtag_clip_bwd_ws_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(self.lib.xtag_clip_bwd(_p(A), _p(Bm), _dt(A), M, N, D, _p(scale), int(label_offset),
+                                     _p(row_lse), _p(col_lse), float(w_row), float(w_col), float(w_diag), _p(g),
+                                     _p(dA), _p(dB), _DT[grad_dtype], _p(dscale), _p(ws), nbytes, self.impl,
+                                     _stream()), "xtag_clip_bwd")
+        return dA, dB, dscale
+
+    def tc_gemm_nt(self, A: torch.Tensor, B: torch.Tensor, out_dtype=torch.float32, alpha: float = 1.0):
+        _cuda(A, B)
+        A, B = A.contiguous(), B.contiguous()
+        M, K = A.shape
+        N = B.shape[0]
+        C = torch.empty((M, N), dtype=out_dtype, device=A.device)
+        check(self.lib.xtag_tc_gemm_nt(_p(A), _p(B), _p(C), _DT[out_dtype], M, N, K, float(alpha), _stream()),
+              "xtag_tc_gemm_nt")
+        return C
+
+    # ---- K4 ----------------------------------------------------------------------------------
+    def xattn_fwd(self, q, k, v, heads: int, softmax_scale: float, dropout_p: float, seed: int, offset: int):
+        """q [b,Lq,H], k/v [b,Lk,H] (last dim contiguous; k and v may be strided views of one buffer)
+        -> (ctx [b,Lq,H], lse [b,heads,Lq])"""
+        _cuda(q, k, v)
+        b, Lq, H = q.shape
+        Lk = k.shape[1]
+        dh = H // heads
+        for t in (q, k, v):
+            assert t.stride(-1) == 1 and t.stride(0) == t.shape[1] * t.stride(1), "rows must be uniformly strided"
+        o = torch.empty((b, Lq, H), dtype=q.dtype, device=q.device)
+        lse = torch.empty((b, heads, Lq), dtype=torch.float32, device=q.device)
+        check(self.lib.xtag_xattn_fwd(_p(q), _p(k), _p(v), _dt(q), _p(o), _p(lse), b, Lq, Lk, heads, dh,
+                                      q.stride(1), k.stride(1), v.stride(1), float(softmax_scale), float(dropout_p),
+                                      int(seed), int(offset), _stream()), "xtag_xattn_fwd")
+        return o, lse
+
+    def xattn_bwd(self, q, k, v, o, do, lse, heads: int, softmax_scale: float, dropout_p: float, seed: int,
+                  offset: int):
+        _cuda(q, k, v, o, do, lse)
+        b, Lq, H = q.shape
+        Lk = k.shape[1]
+        dh = H // heads
+        do = do.contiguous()
+        dq = torch.empty((b, Lq, H), dtype=q.dtype, device=q.device)
+        dk = torch.empty((b, Lk, H), dtype=q.dtype, device=q.device)
+        dv = torch.empty((b, Lk, H), dtype=q.dtype, device=q.device)
+        check(self.lib.xtag_xattn_bwd(_p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _dt(q), _p(dq), _p(dk), _p(dv),
+                                      b, Lq, Lk, heads, dh, q.stride(1), k.stride(1), v.stride(1),
+                                      float(softmax_scale), float(dropout_p), int(seed), int(offset), _stream()),
+              "xtag_xattn_bwd")
+        return dq, dk, dv
+
+    # ---- K5 ----------------------------------------------------------------------------------
+    def asl(self, x: torch.Tensor, y: torch.Tensor, gamma_neg, gamma_pos, clip, eps, want_dx: bool,
+            want_idx: bool):
+        """-> (loss 0-d fp32, dx fp32 | None, idx6 int32 [rows,6] | None)"""
+        _cuda(x, y)
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        y2 = y.reshape(-1, x.shape[-1]).to(torch.float32).contiguous()
+        rows, cols = x2.shape
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        dx = torch.empty((rows, cols), dtype=torch.float32, device=x.device) if want_dx else None
+        idx = torch.empty((rows, 6), dtype=torch.int32, device=x.device) if want_idx else None
+        check(self.lib.xtag_asl_fwd(_p(x2), _dt(x2), _p(y2), rows, cols, float(gamma_neg), float(gamma_pos),
+                                    float(clip or 0.0), float(eps), _p(loss), _p(dx), _p(idx), _stream()),
+              "xtag_asl_fwd")
+        return loss, dx, idx
+
+
+_default: Optional[CudaKernels] = None
+
+
+def default_kernels() -> CudaKernels:
+    global _default
+    if _default is None:
+        _default = CudaKernels()
+    return _default

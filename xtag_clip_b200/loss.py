@@ -1,0 +1,320 @@
+"""Drop-in for the reference's contrastive head: ``ClipLoss``, ``gather_features``, ``create_loss``.
+
+Mirrors /root/reference/src/open_clip/loss.py:21-139 and factory.py:433-469 (same names, argument
+meaning, return values and error behaviour) with the arithmetic replaced by the fused sm_100a
+kernels of libxtag_b200.so (K1 forward, K2 backward).  The B x B logit matrix is never
+materialised; the only collectives are one feature all-gather, one all-gather of the [B] partial
+column log-sum-exps, and (gather_with_grad) one reduce-scatter of the text-feature gradient.
+
+Gradient modes, rank r owns rows/cols R_r = [r*b, (r+1)*b):
+  world_size == 1                     dS = (P_row + P_col - 2*1)/(2B) on the full matrix
+  local_loss, gather_with_grad        rank computes dS[R_r, :] with weights 1/(2b); dI_r is complete
+                                      locally, dT partial [B, D] is reduce-scattered (SUM) -- exactly
+                                      the reference's W x (single-process gradient)
+  local_loss, not gather_with_grad    only the direct local operands carry gradient: dI_r from
+                                      (P_row - 1)[R_r, :], dT_r from (P_col - 1)[:, R_r] (second call
+                                      with the operands swapped)
+  not local_loss                      the full B x B problem on every rank (replicated, as in the
+                                      reference); gather_with_grad reduce-scatters, otherwise the
+                                      local block is sliced out
+
+Documented deviation: with local_loss + gather_with_grad the per-rank ``logit_scale.grad`` is this
+rank's *row block* share  sum_{i in R_r, j} dS_ij S_ij / s, whereas the reference's per-rank value
+mixes the row term of R_r with the column term of R_r.  Their sum over ranks -- what DDP's gradient
+all-reduce produces for the shared ``logit_scale`` parameter -- is identical.
+The upstream gradient of the loss is assumed equal on all ranks (it is for ``loss.backward()`` and
+for GradScaler-scaled losses).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from torch.nn import functional as F
+
+try:
+    import torch.distributed.nn
+    from torch import distributed as dist
+
+    has_distributed = True
+except ImportError:  # pragma: no cover
+    has_distributed = False
+    dist = None
+
+
+# ------------------------------------------------------------------------------------------------
+# plumbing: collectives on the default (or given) process group
+# ------------------------------------------------------------------------------------------------
+class _Comm:
+    def __init__(self, world_size: int, rank: int, group=None):
+        self.world_size, self.rank, self.group = world_size, rank, group
+
+    def all_gather_cat(self, x: torch.Tensor) -> torch.Tensor:
+        """[b, ...] on every rank -> [W*b, ...] in rank order (what torch.cat(all_gather) gives)."""
+        x = x.contiguous()
+        out = torch.empty((self.world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x, group=self.group)
+        return out
+
+    def reduce_scatter_sum(self, x: torch.Tensor) -> torch.Tensor:
+        """[W*b, ...] partials -> [b, ...] = sum over ranks of this rank's block."""
+        x = x.contiguous()
+        b = x.shape[0] // self.world_size
+        out = torch.empty((b,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        if x.is_cuda:
+            dist.reduce_scatter_tensor(out, x, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            # gloo has no reduce_scatter: all_reduce and slice (CPU host-logic tests only)
+            y = x.clone()
+            dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
+            out.copy_(y[self.rank * b:(self.rank + 1) * b])
+        return out
+
+
+@dataclass
+class _Cfg:
+    local_loss: bool
+    gather_with_grad: bool
+    rank: int
+    world_size: int
+    kernels: object
+    comm: Optional[_Comm]
+    comm_dtype: Optional[torch.dtype]
+
+
+def _as_scale_tensor(logit_scale, device) -> torch.Tensor:
+    if torch.is_tensor(logit_scale):
+        return logit_scale.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
+    return torch.full((1,), float(logit_scale), dtype=torch.float32, device=device)
+
+
+class _FusedClipLoss(torch.autograd.Function):
+    """loss = ClipLoss.forward(...) of the reference (loss.py:128-139), all four distributed modes."""
+
+    @staticmethod
+    def forward(ctx, img: torch.Tensor, txt: torch.Tensor, logit_scale, cfg: _Cfg):
+        K, W, r = cfg.kernels, cfg.world_size, cfg.rank
+        scale = _as_scale_tensor(logit_scale, img.device)
+        b = img.shape[0]
+        img_all = txt_all = None
+        if W == 1:
+            off = 0
+            row_lse, col_lse, diag = K.clip_fwd(img, txt, scale, 0)
+        elif cfg.local_loss:
+            off = b * r
+            txt_all = cfg.comm.all_gather_cat(txt)
+            if not cfg.gather_with_grad:
+                img_all = cfg.comm.all_gather_cat(img)       # needed by the swapped backward call
+            row_lse, col_part, diag = K.clip_fwd(img, txt_all, scale, off)
+            parts = cfg.comm.all_gather_cat(col_part.reshape(1, -1))      # [W, B]
+            col_lse = K.lse_combine(parts)
+        else:
+            off = 0
+            img_all = cfg.comm.all_gather_cat(img)
+            txt_all = cfg.comm.all_gather_cat(txt)
+            row_lse, col_lse, diag = K.clip_fwd(img_all, txt_all, scale, 0)
+        loss = K.clip_loss(row_lse, diag, col_lse, off)
+        ctx.cfg, ctx.off, ctx.b = cfg, off, b
+        ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
+        ctx.save_for_backward(img, txt, scale, row_lse, col_lse, img_all, txt_all)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        img, txt, scale, row_lse, col_lse, img_all, txt_all = ctx.saved_tensors
+        cfg, off, b = ctx.cfg, ctx.off, ctx.b
+        K, W = cfg.kernels, cfg.world_size
+        need_i, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_s = ctx.needs_input_grad[2]
+        fdt = img.dtype
+        d_img = d_txt = None
+        if W == 1:
+            B = b
+            d_img, d_txt, ds = K.clip_bwd(img, txt, scale, 0, row_lse, col_lse, 0.5 / B, 0.5 / B, 1.0 / B, g,
+                                          need_i, need_t, fdt)
+        elif cfg.local_loss and cfg.gather_with_grad:
+            cdt = cfg.comm_dtype or fdt
+            d_img, d_txt_all, ds = K.clip_bwd(img, txt_all, scale, off, row_lse, col_lse, 0.5 / b, 0.5 / b, 1.0 / b,
+                                              g, need_i, need_t, cdt if need_t else fdt)
+            if need_i and d_img.dtype != fdt:
+                d_img = d_img.to(fdt)
+            if need_t:
+                d_txt = cfg.comm.reduce_scatter_sum(d_txt_all).to(fdt)
+        elif cfg.local_loss:
+            ds = torch.zeros((), dtype=torch.float32, device=img.device)
+            if need_i or need_s:
+                d_img, _, ds1 = K.clip_bwd(img, txt_all, scale, off, row_lse, col_lse, 0.5 / b, 0.0, 0.5 / b, g,
+                                           need_i, False, fdt)
+                ds = ds + ds1
+            if need_t or need_s:
+                never = torch.full((img_all.shape[0],), float("inf"), dtype=torch.float32, device=img.device)
+                d_txt, _, ds2 = K.clip_bwd(txt, img_all, scale, off, col_lse[off:off + b].contiguous(), never,
+                                           0.5 / b, 0.0, 0.5 / b, g, need_t, False, fdt)
+                ds = ds + ds2
+        else:
+            B = img_all.shape[0]
+            cdt = (cfg.comm_dtype or fdt) if cfg.gather_with_grad else fdt
+            d_ia, d_ta, ds = K.clip_bwd(img_all, txt_all, scale, 0, row_lse, col_lse, 0.5 / B, 0.5 / B, 1.0 / B, g,
+                                        need_i, need_t, cdt)
+            if cfg.gather_with_grad:
+                d_img = cfg.comm.reduce_scatter_sum(d_ia).to(fdt) if need_i else None
+                d_txt = cfg.comm.reduce_scatter_sum(d_ta).to(fdt) if need_t else None
+            else:
+                lo, hi = cfg.rank * b, (cfg.rank + 1) * b
+                d_img = d_ia[lo:hi].contiguous() if need_i else None
+                d_txt = d_ta[lo:hi].contiguous() if need_t else None
+        d_scale = None
+        if need_s and ctx.scale_meta is not None:
+            shape, dtype = ctx.scale_meta
+            d_scale = ds.to(dtype).reshape(shape)
+        return d_img, d_txt, d_scale, None
+
+
+# ------------------------------------------------------------------------------------------------
+# reference API
+# ------------------------------------------------------------------------------------------------
+def gather_features(
+        image_features,
+        text_features,
+        local_loss=False,
+        gather_with_grad=False,
+        rank=0,
+        world_size=1,
+        use_horovod=False
+):
+    """Same contract as the reference's ``gather_features`` (loss.py:21-65): returns
+    ``(all_image_features, all_text_features)``, the per-rank blocks concatenated in rank order,
+    autograd-connected exactly as the reference (see module docstring).  This is the materialising
+    helper kept for API compatibility (``get_logits`` and subclasses use it); the fused
+    ``ClipLoss.forward`` does its own gather."""
+    assert has_distributed, 'torch.distributed did not import correctly, please use a PyTorch version with support.'
+    if use_horovod:
+        raise NotImplementedError("Horovod is not available in xtag_clip_b200 (NCCL/torch.distributed only)")
+    if gather_with_grad:
+        all_image_features = torch.cat(torch.distributed.nn.all_gather(image_features), dim=0)
+        all_text_features = torch.cat(torch.distributed.nn.all_gather(text_features), dim=0)
+    else:
+        comm = _Comm(world_size, rank)
+        with torch.no_grad():
+            gi = list(comm.all_gather_cat(image_features).chunk(world_size, dim=0))
+            gt = list(comm.all_gather_cat(text_features).chunk(world_size, dim=0))
+        if not local_loss:
+            # ensure grads for local rank when all_* features don't have a gradient
+            gi[rank] = image_features
+            gt[rank] = text_features
+        all_image_features = torch.cat(gi, dim=0)
+        all_text_features = torch.cat(gt, dim=0)
+    return all_image_features, all_text_features
+
+
+class ClipLoss(nn.Module):
+    """``ClipLoss(local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
+    use_horovod=False)`` -- reference signature (loss.py:68-89).  ``forward(image_features,
+    text_features, logit_scale, output_dict=False)`` returns a 0-d fp32 tensor or
+    ``{"contrastive_loss": tensor}`` (loss.py:128-139)."""
+
+    def __init__(
+            self,
+            local_loss=False,
+            gather_with_grad=False,
+            cache_labels=False,
+            rank=0,
+            world_size=1,
+            use_horovod=False,
+            *,
+            group=None,
+            comm_dtype: Optional[torch.dtype] = None,
+            _kernels=None,
+    ):
+        super().__init__()
+        if use_horovod:
+            raise NotImplementedError("use_horovod=True: Horovod is not supported by xtag_clip_b200; "
+                                      "use torch.distributed (NCCL)")
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.use_horovod = use_horovod
+        self._group = group
+        self._comm_dtype = comm_dtype
+        self._kernels = _kernels
+
+        # cache state
+        self.prev_num_logits = 0
+        self.labels = {}
+
+    # -- helpers kept for API compatibility (CoCaLoss / DistillClipLoss call them, loss.py:170, 202-208)
+    def get_ground_truth(self, device, num_logits) -> torch.Tensor:
+        if self.prev_num_logits != num_logits or device not in self.labels:
+            labels = torch.arange(num_logits, device=device, dtype=torch.long)
+            if self.world_size > 1 and self.local_loss:
+                labels = labels + num_logits * self.rank
+            if self.cache_labels:
+                self.labels[device] = labels
+                self.prev_num_logits = num_logits
+        else:
+            labels = self.labels[device]
+        return labels
+
+    def get_logits(self, image_features, text_features, logit_scale):
+        """Materialising slow path with the reference's exact expressions (loss.py:104-126).
+        Not used by ``forward``."""
+        if self.world_size > 1:
+            all_image_features, all_text_features = gather_features(
+                image_features, text_features,
+                local_loss=self.local_loss, gather_with_grad=self.gather_with_grad,
+                rank=self.rank, world_size=self.world_size, use_horovod=self.use_horovod)
+            if self.local_loss:
+                logits_per_image = logit_scale * image_features @ all_text_features.T
+                logits_per_text = logit_scale * text_features @ all_image_features.T
+            else:
+                logits_per_image = logit_scale * all_image_features @ all_text_features.T
+                logits_per_text = logits_per_image.T
+        else:
+            logits_per_image = logit_scale * image_features @ text_features.T
+            logits_per_text = logit_scale * text_features @ image_features.T
+        return logits_per_image, logits_per_text
+
+    def _cfg(self) -> _Cfg:
+        k = self._kernels
+        if k is None:
+            from .kernels import default_kernels
+            k = default_kernels()
+        comm = None
+        if self.world_size > 1:
+            assert has_distributed, 'torch.distributed did not import correctly, please use a PyTorch version with support.'
+            comm = _Comm(self.world_size, self.rank, self._group)
+        return _Cfg(self.local_loss, self.gather_with_grad, self.rank, self.world_size, k, comm, self._comm_dtype)
+
+    def forward(self, image_features, text_features, logit_scale, output_dict=False):
+        if image_features.dim() != 2 or image_features.shape != text_features.shape:
+            raise ValueError(f"image_features {tuple(image_features.shape)} and text_features "
+                             f"{tuple(text_features.shape)} must both be [batch, dim]")
+        # one compute dtype for both operands: bf16 stays bf16 (tcgen05 path), anything else -> fp32
+        if image_features.dtype == text_features.dtype and image_features.dtype != torch.float16:
+            img, txt = image_features, text_features
+        else:
+            img, txt = image_features.float(), text_features.float()
+        total_loss = _FusedClipLoss.apply(img.contiguous(), txt.contiguous(), logit_scale, self._cfg())
+        return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+
+def create_loss(args):
+    """Reference factory contract (factory.py:433-469) for the losses in scope: returns the fused
+    ``ClipLoss`` configured from ``args.local_loss / gather_with_grad / rank / world_size / horovod``.
+    Distill / CoCa / SigLIP losses are outside the hot path."""
+    if getattr(args, "distill", False) or getattr(args, "siglip", False) or \
+            "coca" in str(getattr(args, "model", "")).lower():
+        raise NotImplementedError("xtag_clip_b200.create_loss covers the ClipLoss path only "
+                                  "(--distill / --siglip / coca models are out of scope)")
+    return ClipLoss(
+        local_loss=args.local_loss,
+        gather_with_grad=args.gather_with_grad,
+        cache_labels=True,
+        rank=args.rank,
+        world_size=args.world_size,
+        use_horovod=args.horovod,
+    )

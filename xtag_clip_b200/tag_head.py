@@ -1,0 +1,251 @@
+"""Drop-in for the XTag cross-attention tag head (``CLIP.tag_forward``) and the feature epilogue.
+
+Mirrors, with the same parameter names so a reference ``state_dict`` loads unchanged
+(35 ``tag_*`` keys):
+  * /root/reference/src/open_clip/model.py:270-288   construction (BertModel minus embeddings and
+    self-attention, ``tag_labels`` Embedding(44, 768), ``tag_fc`` Linear(768, 1))
+  * model.py:337-352                                   ``tag_forward(tag_embeds [b,N,D]) -> [b,44]``
+  * tagging_heads/bert.py:189-278, 281-292, 344-370, 386-456   the tagging-mode layer
+  * model.py:311-313, 332-333                          ``F.normalize`` epilogue -> ``l2_normalize``
+  * model.py:354-383                                   ``prepare_control_words``
+
+What runs where: the attention core (QK^T, softmax, dropout, PV) is the fused CUDA kernel K4; the
+L2-normalise is K3; the dense projections / LayerNorm / GELU stay torch library calls in v1
+("stays cuBLAS / torch in v1").  Layer-0 queries do not depend on the sample
+(model.py:342 repeats the same ``tag_labels.weight``), so Q-projection of layer 0 is computed once
+per call on [44, 768] instead of [b, 44, 768].
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+TAG_HIDDEN = 768
+TAG_HEADS = 4
+TAG_LAYERS = 2
+TAG_FF = 3072
+TAG_LN_EPS = 1e-12
+TAG_QUERIES = 44
+TAG_DROPOUT = 0.1
+CATEGORY_SIZES = (3, 4, 3, 4, 4, 4)
+
+
+def _kernels(k=None):
+    if k is not None:
+        return k
+    from .kernels import default_kernels
+    return default_kernels()
+
+
+# ---- K3 -------------------------------------------------------------------------------------------
+class _L2Normalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eps, out_dtype, kernels):
+        K = _kernels(kernels)
+        y, inv, _ = K.l2norm_fwd(x, out_dtype or x.dtype, eps)
+        ctx.save_for_backward(y, inv)
+        ctx.meta = (K, eps, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        y, inv = ctx.saved_tensors
+        K, eps, in_dtype = ctx.meta
+        return K.l2norm_bwd(gy, y, inv, in_dtype, eps), None, None, None
+
+
+def l2_normalize(x: torch.Tensor, eps: float = 1e-12, out_dtype: Optional[torch.dtype] = None, *, _kernels=None):
+    """``F.normalize(x, dim=-1)`` (model.py:313, 333) with an optional fused cast of the output."""
+    return _L2Normalize.apply(x, eps, out_dtype, _kernels)
+
+
+# ---- K4 -------------------------------------------------------------------------------------------
+class _CrossAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, heads, dropout_p, seed, offset, kernels):
+        K = _kernels(kernels)
+        scale = 1.0 / math.sqrt(q.shape[-1] // heads)
+        o, lse = K.xattn_fwd(q, k, v, heads, scale, dropout_p, seed, offset)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.meta = (K, heads, scale, dropout_p, seed, offset)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        K, heads, scale, dropout_p, seed, offset = ctx.meta
+        dq, dk, dv = K.xattn_bwd(q, k, v, o, do, lse, heads, scale, dropout_p, seed, offset)
+        return dq, dk, dv, None, None, None, None, None
+
+
+def cross_attention(q, k, v, heads: int, dropout_p: float = 0.0, seed: int = 0, offset: int = 0, *, _kernels=None):
+    """softmax(q k^T / sqrt(dh)) v per (sample, head) -- bert.py:219-274.  q [b,Lq,H], k/v [b,Lk,H]."""
+    if q.dtype == torch.float16:          # fp16 autocast: run the exact fp32 kernel
+        q, k, v = q.float(), k.float(), v.float()
+    return _CrossAttention.apply(q.contiguous(), k, v, heads, dropout_p, seed, offset, _kernels)
+
+
+# ---- module tree with the reference's parameter names --------------------------------------------
+class _SelfAttn(nn.Module):          # crossattention.self
+    def __init__(self, encoder_width: int):
+        super().__init__()
+        self.query = nn.Linear(TAG_HIDDEN, TAG_HIDDEN)
+        self.key = nn.Linear(encoder_width, TAG_HIDDEN)
+        self.value = nn.Linear(encoder_width, TAG_HIDDEN)
+
+
+class _SelfOutput(nn.Module):        # crossattention.output / (layer).output
+    def __init__(self, in_features: int):
+        super().__init__()
+        self.dense = nn.Linear(in_features, TAG_HIDDEN)
+        self.LayerNorm = nn.LayerNorm(TAG_HIDDEN, eps=TAG_LN_EPS)
+
+
+class _CrossAttnBlock(nn.Module):    # crossattention
+    def __init__(self, encoder_width: int):
+        super().__init__()
+        self.self = _SelfAttn(encoder_width)
+        self.output = _SelfOutput(TAG_HIDDEN)
+
+
+class _Intermediate(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.dense = nn.Linear(TAG_HIDDEN, TAG_FF)
+
+
+class _TagLayer(nn.Module):
+    def __init__(self, encoder_width: int):
+        super().__init__()
+        self.crossattention = _CrossAttnBlock(encoder_width)
+        self.intermediate = _Intermediate()
+        self.output = _SelfOutput(TAG_FF)
+
+
+class _TagEncoder(nn.Module):
+    def __init__(self, encoder_width: int):
+        super().__init__()
+        self.layer = nn.ModuleList([_TagLayer(encoder_width) for _ in range(TAG_LAYERS)])
+
+
+class _TagBert(nn.Module):
+    def __init__(self, encoder_width: int):
+        super().__init__()
+        self.encoder = _TagEncoder(encoder_width)
+
+
+class TagHead(nn.Module):
+    """Holds ``tag_head``, ``tag_labels``, ``tag_fc`` under the reference's names and implements
+    ``tag_forward``.  Use ``TagHead.from_reference(model)`` / ``load_state_dict(filtered)`` to take over the
+    weights of a reference ``CLIP`` and ``patch_reference_model(model)`` to route ``model.tag_forward`` here."""
+
+    def __init__(self, embed_dim: int, tag_list: Optional[List[str]] = None, *, _kernels=None):
+        super().__init__()
+        self.tag_head = _TagBert(embed_dim)
+        self.tag_labels = nn.Embedding(TAG_QUERIES, TAG_HIDDEN)
+        self.tag_fc = nn.Linear(TAG_HIDDEN, 1)
+        self.tag_list = list(tag_list) if tag_list is not None else None
+        self.embed_dim = embed_dim
+        self._k = _kernels
+        self._step = 0
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # BertPreTrainedModel._init_weights (bert.py:631-641): N(0, 0.02) weights, zero biases, unit LayerNorm
+        for m in self.tag_head.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, mean=0.0, std=0.02)
+                nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    @classmethod
+    def from_reference(cls, model: nn.Module, **kw) -> "TagHead":
+        sd = {k: v for k, v in model.state_dict().items() if k.startswith(("tag_head.", "tag_labels.", "tag_fc."))}
+        d = sd["tag_head.encoder.layer.0.crossattention.self.key.weight"].shape[1]
+        head = cls(d, getattr(model, "tag_list", None), **kw)
+        head.load_state_dict(sd, strict=True)
+        p = next(iter(sd.values()))
+        return head.to(device=p.device)
+
+    def tag_forward(self, tag_embeds: torch.Tensor, seed: Optional[int] = None) -> torch.Tensor:
+        """tokens [b, N, D] -> tag logits [b, 44]  (model.py:337-352)."""
+        if tag_embeds.dim() != 3 or tag_embeds.shape[-1] != self.embed_dim:
+            raise ValueError(f"tag_embeds must be [b, N, {self.embed_dim}], got {tuple(tag_embeds.shape)}")
+        bs = tag_embeds.shape[0]
+        drop = TAG_DROPOUT if self.training else 0.0
+        if seed is None:
+            seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+        self._step += 1
+        h = None                                   # layer-0 hidden state is the shared label embedding
+        label = self.tag_labels.weight             # [44, 768]
+        for li, layer in enumerate(self.tag_head.encoder.layer):
+            ca = layer.crossattention
+            if h is None:
+                q = ca.self.query(label).unsqueeze(0).expand(bs, -1, -1)     # once, not per sample
+                resid = label.unsqueeze(0)
+            else:
+                q = ca.self.query(h)
+                resid = h
+            k = ca.self.key(tag_embeds)
+            v = ca.self.value(tag_embeds)
+            ctx = cross_attention(q, k, v, TAG_HEADS, drop, seed, self._step * TAG_LAYERS + li, _kernels=self._k)
+            a = F.dropout(ca.output.dense(ctx.to(k.dtype)), drop, self.training)
+            a = ca.output.LayerNorm(a + resid)
+            f = F.gelu(layer.intermediate.dense(a))
+            o = F.dropout(layer.output.dense(f), drop, self.training)
+            h = layer.output.LayerNorm(o + a)
+        return self.tag_fc(h).squeeze(-1)
+
+    forward = tag_forward
+
+    def control_word_indices(self, tag_logits: torch.Tensor) -> torch.Tensor:
+        """int64 [b, 6]: per category the top-1 tag index (model.py:362-370)."""
+        n = TAG_QUERIES // 2
+        s = tag_logits.sigmoid()
+        out, pos = [], 0
+        for size in CATEGORY_SIZES:
+            score = s[:, pos:pos + size] + s[:, n + pos:n + pos + size]
+            out.append(torch.argsort(score, dim=-1, descending=True)[:, :1] + pos)
+            pos += size
+        return torch.cat(out, dim=-1)
+
+    def prepare_control_words(self, tag_logits: torch.Tensor, samples=None) -> List[str]:
+        """list[str], tags joined by ',' (model.py:354-383).  One device->host transfer of [b,6] ints."""
+        if self.tag_list is None:
+            raise RuntimeError("TagHead.tag_list is not set (pass the model's tag_list)")
+        idx = self.control_word_indices(tag_logits).tolist()
+        return [",".join(self.tag_list[i] for i in row) for row in idx]
+
+
+def patch_reference_model(model: nn.Module, *, _kernels=None) -> nn.Module:
+    """Route ``model.tag_forward`` (and ``encode_*``'s normalise, via ``model.xtag_normalize``) of a
+    reference ``open_clip.CLIP`` instance through this package WITHOUT adding parameters or
+    buffers: the fused head reads the model's own ``tag_head`` / ``tag_labels`` / ``tag_fc`` weights."""
+    head = TagHead.__new__(TagHead)
+    nn.Module.__init__(head)
+    # share (not copy) the reference modules' parameters
+    object.__setattr__(head, "_ref", model)
+    head.embed_dim = model.tag_head.encoder.layer[0].crossattention.self.key.weight.shape[1]
+    head.tag_list = getattr(model, "tag_list", None)
+    head._k, head._step = _kernels, 0
+
+    def tag_forward(tag_embeds):
+        head.__dict__["training"] = model.training
+        head._modules["tag_head"] = model.tag_head
+        head._modules["tag_labels"] = model.tag_labels
+        head._modules["tag_fc"] = model.tag_fc
+        try:
+            return TagHead.tag_forward(head, tag_embeds)
+        finally:
+            for n in ("tag_head", "tag_labels", "tag_fc"):
+                head._modules.pop(n, None)
+
+    model.tag_forward = tag_forward
+    model.xtag_normalize = lambda x: l2_normalize(x, _kernels=_kernels)
+    return model
