@@ -50,6 +50,11 @@ const char* xtag_last_error(void);
 int         xtag_device_check(void);
 /* number of kernels launched by this library in this process (bench.py's gpu_launches) */
 uint64_t    xtag_launch_count(void);
+/* Diagnostics for bench.py's roofline: while enabled, every tcgen05 launch is bracketed by CUDA events on
+ * its stream.  xtag_prof_read synchronises them and returns up to `cap` records: tag (0 = K1 forward,
+ * 1 = K2 dS producer, 2 = plain GEMM), duration in ms, algorithmic FLOPs (2*M*N*K).  enable(0/1) clears. */
+int         xtag_prof_enable(int on);
+int         xtag_prof_read(int* tags_host, float* ms_host, double* flops_host, int cap);
 
 /* ---------------------------------------------------------------------------------------------
  * K3  fused L2-normalise + cast.   Replaces F.normalize(features, dim=-1) in

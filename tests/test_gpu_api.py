@@ -1,0 +1,190 @@
+"""GPU parity tests, API level: the reference-facing Python API (ClipLoss / TagHead / AsymmetricLoss / l2_normalize)
+running on the CUDA library, against the golden fixtures (reference outputs) and the oracle; plus full-size
+(BASELINE config) property / known-answer tests where the oracle would take minutes."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import xtag_clip_b200 as xt
+from oracle.tag_oracle import make_tag_params
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().double().cpu().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def feats(seed, b, d, corr=0.3):
+    g = torch.Generator().manual_seed(seed)
+    i = torch.randn(b, d, generator=g)
+    n = torch.randn(b, d, generator=g)
+    t = corr * i + (1 - corr) * n
+    return torch.nn.functional.normalize(i, dim=-1), torch.nn.functional.normalize(t, dim=-1)
+
+
+def test_cliploss_fp32_mode_golden(golden_dir):
+    """fp32 inputs -> exact SIMT path; bar 1e-5 against the reference's own outputs."""
+    g = np.load(os.path.join(golden_dir, "clip_w1.npz"))
+    for n in range(int(g["n_cases"])):
+        pre = f"c{n}_f64_"
+        I = torch.from_numpy(g[pre + "I"]).float().cuda().requires_grad_(True)
+        T = torch.from_numpy(g[pre + "T"]).float().cuda().requires_grad_(True)
+        s = torch.tensor(float(g[pre + "scale"]), device="cuda", requires_grad=True)
+        loss = xt.ClipLoss()(I, T, s)
+        assert loss.dtype == torch.float32 and loss.dim() == 0 and loss.is_cuda
+        loss.backward()
+        assert rel_err(loss, g[pre + "loss"]) < 1e-5
+        assert rel_err(I.grad, g[pre + "dI"]) < 1e-5
+        assert rel_err(T.grad, g[pre + "dT"]) < 1e-5
+        assert abs(s.grad.item() - float(g[pre + "dscale"])) < 1e-3 * abs(float(g[pre + "dscale"])) + 2e-5
+
+
+@pytest.mark.parametrize("B,D,scale", [(256, 512, 14.285714), (1024, 512, 14.285714), (1024, 512, 100.0),
+                                       (2048, 512, 14.285714), (4096, 512, 14.285714), (1000, 768, 30.0)])
+def test_cliploss_bf16_config2_vs_oracle(B, D, scale):
+    """BASELINE config 2 (ViT-B-32 head sweep, D=512, bf16): loss <= 1e-3, grads <= 2e-2 vs the oracle evaluated in
+    fp64 on the SAME bf16-rounded inputs."""
+    I, T = feats(B + D, B, D, corr=0.15 if scale > 50 else 0.4)
+    Ib, Tb = I.bfloat16(), T.bfloat16()
+    Ic = Ib.cuda().requires_grad_(True)
+    Tc = Tb.cuda().requires_grad_(True)
+    s = torch.tensor(scale, device="cuda", requires_grad=True)
+    out = xt.ClipLoss()(Ic, Tc, s, output_dict=True)
+    out["contrastive_loss"].backward()
+    assert Ic.grad.dtype == torch.bfloat16
+    torch.set_num_threads(os.cpu_count() or 8)
+    lo, dI, dT, ds, _, _ = oracle.clip_loss_closed_form(Ib.double(), Tb.double(), torch.tensor(scale, dtype=torch.float64))
+    assert rel_err(out["contrastive_loss"], lo) < 1e-3
+    assert rel_err(Ic.grad, dI) < 2e-2
+    assert rel_err(Tc.grad, dT) < 2e-2
+    assert abs(s.grad.item() - ds.item()) < 2e-2 * abs(ds.item()) + 2e-5
+
+
+def test_cliploss_fp16_and_mixed_inputs_upcast():
+    I, T = feats(3, 64, 32)
+    a = xt.ClipLoss()(I.half().cuda(), T.half().cuda(), 10.0)
+    b = oracle.clip_loss_single(I.half().double(), T.half().double(), torch.tensor(10.0, dtype=torch.float64))
+    assert rel_err(a, b) < 1e-5
+    c = xt.ClipLoss()(I.bfloat16().cuda(), T.cuda(), 10.0)       # mixed -> fp32
+    d = oracle.clip_loss_single(I.bfloat16().double(), T.double(), torch.tensor(10.0, dtype=torch.float64))
+    assert rel_err(c, d) < 1e-5
+
+
+def test_cliploss_full_size_known_answer():
+    """BASELINE config 5 shape on one GPU (B=32768, D=1024, bf16): one-hot features I_i = T_i = e_{i mod D} have a
+    closed-form loss and gradient: S_ij = s if i == j (mod D) else 0."""
+    B, D, s = 32768, 1024, 5.0
+    idx = torch.arange(B, device="cuda") % D
+    I = torch.zeros(B, D, device="cuda", dtype=torch.bfloat16)
+    I[torch.arange(B, device="cuda"), idx] = 1.0
+    T = I.clone()
+    I.requires_grad_(True)
+    T.requires_grad_(True)
+    sc = torch.tensor(s, device="cuda", requires_grad=True)
+    loss = xt.ClipLoss()(I, T, sc)
+    loss.backward()
+    r = B // D
+    Z = r * math.exp(s) + (B - r)
+    expect = math.log(Z) - s
+    assert abs(loss.item() - expect) < 1e-3 * expect
+    # dS_ij = (P_row + P_col - 2 delta)/(2B) with P_row = P_col = e^{S_ij}/Z  =>  dI_i = s * [ (2 r e^s/Z - 2)/(2B) e_c(i)
+    #                                                                        + sum_{c != c(i)} (2 r / Z)/(2B) e_c ]
+    on = s * (2 * r * math.exp(s) / Z - 2) / (2 * B)
+    off = s * (2 * r / Z) / (2 * B)
+    gi = I.grad.float()
+    assert rel_err(gi[torch.arange(B, device="cuda"), idx], torch.full((B,), on)) < 2e-2
+    sel = torch.ones(B, D, dtype=torch.bool, device="cuda")
+    sel[torch.arange(B, device="cuda"), idx] = False
+    assert abs(gi[sel].mean().item() - off) < 2e-2 * off and abs(gi[sel].max().item() - off) < 5e-2 * off
+    assert rel_err(T.grad.float(), gi) < 1e-2                       # symmetric problem
+    ds = ((2 * r * math.exp(s) / Z - 2) / (2 * B)) * B               # sum_ij dS_ij S_ij / s: only S_ij = s entries count
+    # off-diagonal (mod D) entries have S = 0; per row r entries at s: r*(2 e^s/Z)/(2B) - 2/(2B)
+    assert abs(sc.grad.item() - ds) < 2e-2 * abs(ds)
+
+
+def test_cliploss_full_size_properties():
+    """Size-independent identities at B=32768, D=1024 (random bf16 features):
+       <I, dI> = <T, dT> = s * d(logit_scale)   (dI = s dS T, dT = s dS^T I, ds = sum dS.S / s)
+       swapping the roles of image and text leaves the loss unchanged and swaps the gradients."""
+    B, D, s = 32768, 1024, 14.285714
+    I, T = feats(77, B, D, corr=0.3)
+    I, T = I.bfloat16().cuda(), T.bfloat16().cuda()
+    Ia, Ta = I.clone().requires_grad_(True), T.clone().requires_grad_(True)
+    sa = torch.tensor(s, device="cuda", requires_grad=True)
+    la = xt.ClipLoss()(Ia, Ta, sa)
+    la.backward()
+    ii = (Ia.grad.float() * I.float()).sum().item()
+    tt = (Ta.grad.float() * T.float()).sum().item()
+    assert abs(ii - tt) < 2e-2 * abs(ii) + 1e-5
+    assert abs(ii - s * sa.grad.item()) < 2e-2 * abs(ii) + 1e-5
+    Ib, Tb = T.clone().requires_grad_(True), I.clone().requires_grad_(True)
+    lb = xt.ClipLoss()(Ib, Tb, torch.tensor(s, device="cuda"))
+    lb.backward()
+    assert abs(la.item() - lb.item()) < 1e-4 * la.item()
+    assert rel_err(Ib.grad, Ta.grad) < 2e-2 and rel_err(Tb.grad, Ia.grad) < 2e-2
+    assert 0.0 < la.item() < math.log(B)
+
+
+def test_tag_head_golden_fp32(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tag_head.npz"))
+    for n in range(int(g["n_cases"])):
+        pre = f"t{n}_"
+        seed, D, b, N, gain = g[pre + "cfg"]
+        params = make_tag_params(int(seed), int(D), gain=float(gain), dtype=torch.float32)
+        head = xt.TagHead(int(D), tag_list=list(g[pre + "tag_list"])).cuda()
+        head.load_state_dict(params, strict=True)
+        head.eval()
+        tokens = torch.from_numpy(g[pre + "tokens"]).float().cuda().requires_grad_(True)
+        torch.backends.cuda.matmul.allow_tf32 = False      # the dense layers are torch library calls
+        logits = head.tag_forward(tokens)
+        logits.backward(torch.from_numpy(g[pre + "glogits"]).float().cuda())
+        assert rel_err(logits, g[pre + "logits"]) < 2e-5
+        assert rel_err(tokens.grad, g[pre + "dtokens"]) < 1e-4
+        assert head.prepare_control_words(logits.detach()) == list(g[pre + "words"])
+
+
+def test_tag_head_bf16_config3_shape():
+    """BASELINE config 3 shape (tokens [b,197,512], b reduced to keep the fp64 oracle in seconds), bf16 autocast
+    as the reference trains (precision amp_bf16)."""
+    D, b, N = 512, 32, 197
+    params = make_tag_params(7, D, gain=4.0, dtype=torch.float32)
+    head = xt.TagHead(D).cuda()
+    head.load_state_dict(params, strict=True)
+    head.eval()
+    g = torch.Generator().manual_seed(8)
+    tokens = torch.randn(b, N, D, generator=g)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = head.tag_forward(tokens.cuda())
+    p64 = {k: v.double() for k, v in params.items()}
+    ref = oracle.tag_head_forward(tokens.double(), p64)
+    assert rel_err(logits.float(), ref) < 3e-2
+
+
+def test_asymmetric_loss_and_l2_api(golden_dir):
+    g = np.load(os.path.join(golden_dir, "asl.npz"))
+    x = torch.from_numpy(g["x"]).float().cuda().requires_grad_(True)
+    loss = xt.AsymmetricLoss()(x, torch.from_numpy(g["y"]).float())
+    (2.0 * loss).backward()
+    assert rel_err(loss, g["k0_loss"]) < 1e-5 and rel_err(x.grad, 2.0 * g["k0_dx"]) < 1e-5
+    gl = np.load(os.path.join(golden_dir, "l2norm.npz"))
+    xx = torch.from_numpy(gl["x"]).float().cuda().requires_grad_(True)
+    y = xt.l2_normalize(xx)
+    y.backward(torch.from_numpy(gl["gy"]).float().cuda())
+    assert rel_err(y, gl["y"]) < 1e-6
+    rows = [0, 1, 3, 4, 6, 7, 8]
+    assert rel_err(xx.grad[rows], gl["gx"][rows]) < 1e-5
+
+
+def test_launch_counter_counts_native_kernels():
+    from xtag_clip_b200 import _lib
+    n0 = _lib.launch_count()
+    I, T = feats(1, 256, 512)
+    xt.ClipLoss()(I.bfloat16().cuda(), T.bfloat16().cuda(), 10.0)
+    assert _lib.launch_count() - n0 >= 4          # tcgen05 fwd + 2 reductions + loss

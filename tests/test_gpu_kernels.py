@@ -1,0 +1,224 @@
+"""GPU parity tests, kernel level: every C entry point of libxtag_b200.so (called through the ctypes wrappers in
+xtag_clip_b200/kernels.py, i.e. through the C ABI) against the contract model / the oracle on the same seeded
+inputs.  Bars: fp32 path <= 1e-5 (max-norm relative), bf16 tcgen05 path: loss 1e-3, grads 2e-2 (BASELINE.json)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from kernel_model import ModelKernels
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().double().cpu().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def K():
+    from xtag_clip_b200.kernels import CudaKernels
+    k = CudaKernels()
+    assert k.lib.xtag_device_check() == 0, k.lib.xtag_last_error()
+    return k
+
+
+@pytest.fixture(scope="module")
+def MK():
+    return ModelKernels()
+
+
+def feats(seed, b, d, corr=0.3, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    i = torch.randn(b, d, generator=g)
+    n = torch.randn(b, d, generator=g)
+    t = corr * i + (1 - corr) * n
+    i = torch.nn.functional.normalize(i, dim=-1)
+    t = torch.nn.functional.normalize(t, dim=-1)
+    return i.to(dtype), t.to(dtype)
+
+
+# ---------------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("rows,dim", [(9, 24), (16, 512), (1000, 768), (4096, 1024), (7, 13)])
+@pytest.mark.parametrize("in_dt,out_dt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                          (torch.bfloat16, torch.bfloat16)])
+def test_l2norm(K, MK, rows, dim, in_dt, out_dt):
+    g = torch.Generator().manual_seed(rows * 7 + dim)
+    x = (torch.randn(rows, dim, generator=g) * 3).to(in_dt)
+    if rows > 3:
+        x[2] = 0
+    y, inv, yT = K.l2norm_fwd(x.cuda(), out_dt, 1e-12, want_transposed=True)
+    ym, invm, _ = MK.l2norm_fwd(x, out_dt, 1e-12)
+    tol = 1e-6 if out_dt == torch.float32 else 8e-3
+    assert rel_err(y, ym) < tol
+    assert rel_err(inv[inv < 1e11], invm[invm < 1e11]) < 1e-5
+    assert torch.equal(yT, y.T.contiguous())
+    gy = torch.randn(rows, dim, generator=g).to(out_dt)
+    gx = K.l2norm_bwd(gy.cuda(), y, inv, in_dt, 1e-12)
+    gxm = MK.l2norm_bwd(gy, y.cpu(), inv.cpu(), in_dt, 1e-12)
+    ok = (inv < 1e11).cpu()
+    assert rel_err(gx.cpu()[ok], gxm[ok]) < (1e-5 if in_dt == torch.float32 else 1e-2)
+
+
+def test_l2norm_golden(K, golden_dir):
+    g = np.load(os.path.join(golden_dir, "l2norm.npz"))
+    x = torch.from_numpy(g["x"]).float().cuda()
+    y, inv, _ = K.l2norm_fwd(x, torch.float32, 1e-12)
+    assert rel_err(y, g["y"]) < 1e-6
+    gx = K.l2norm_bwd(torch.from_numpy(g["gy"]).float().cuda(), y, inv, torch.float32, 1e-12)
+    rows = [0, 1, 3, 4, 6, 7, 8]
+    assert rel_err(gx[rows], g["gx"][rows]) < 1e-5
+    assert rel_err(gx[[2, 5]], g["gx"][[2, 5]]) < 1e-5      # clamped rows: gy / eps
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("M,N,Kd", [(128, 256, 64), (128, 256, 256), (256, 512, 128), (200, 300, 72), (44, 40, 8),
+                                    (1024, 1024, 512), (4096, 1024, 4096)])
+def test_tc_gemm_nt(K, M, N, Kd):
+    g = torch.Generator().manual_seed(M + N + Kd)
+    A = torch.randn(M, Kd, generator=g).bfloat16().cuda()
+    B = torch.randn(N, Kd, generator=g).bfloat16().cuda()
+    ref = A.float() @ B.float().T
+    C = K.tc_gemm_nt(A, B, torch.float32, 0.5)
+    assert rel_err(C, 0.5 * ref) < 2e-5
+    Cb = K.tc_gemm_nt(A, B, torch.bfloat16, 1.0)
+    assert rel_err(Cb, ref) < 6e-3
+
+
+# ---------------------------------------------------------------------------------------------- K1 / K2 kernels
+SHAPES = [(16, 16, 32, 0), (64, 64, 64, 0), (33, 47, 40, 5), (130, 300, 72, 100), (256, 256, 512, 0),
+          (128, 1024, 512, 384), (1024, 1024, 512, 0)]
+
+
+@pytest.mark.parametrize("impl,dtype", [(1, torch.float32), (1, torch.bfloat16), (2, torch.bfloat16)])
+@pytest.mark.parametrize("M,N,D,off", SHAPES)
+@pytest.mark.parametrize("scale", [14.285714, 100.0])
+def test_clip_fwd_bwd_kernels(MK, impl, dtype, M, N, D, off, scale):
+    from xtag_clip_b200.kernels import CudaKernels
+    K = CudaKernels(impl=impl)
+    I, _ = feats(M * 3 + D, max(M, N), D, corr=0.2 if scale > 50 else 0.5, dtype=dtype)
+    _, T = feats(M * 3 + D, max(M, N), D, corr=0.2 if scale > 50 else 0.5, dtype=dtype)
+    A = I[:M].contiguous()
+    # make the label pairs (i, i+off) the correlated ones
+    Bm = torch.roll(T[:N], shifts=off, dims=0).contiguous() if off else T[:N].contiguous()
+    s = torch.tensor([scale])
+    row, col, diag = K.clip_fwd(A.cuda(), Bm.cuda(), s.cuda(), off)
+    rm, cm, dm = MK.clip_fwd(A, Bm, s, off)
+    # LSEs are O(scale); the loss tolerance is what matters: 1e-5 (fp32) / 1e-3 (tcgen05, approx exp2)
+    tol = 5e-6 if impl == 1 else 2e-5
+    assert rel_err(row, rm) < tol and rel_err(col, cm) < tol and rel_err(diag, dm) < tol
+    loss = K.clip_loss(row, diag, col, off)
+    lm = MK.clip_loss(rm, dm, cm, off)
+    assert rel_err(loss, lm) < (1e-5 if impl == 1 else 1e-3)
+    # backward with the exact LSEs so only the backward kernel is under test
+    g = torch.tensor(0.7)
+    w = (0.5 / M, 0.5 / M, 1.0 / M)
+    gd = torch.float32 if dtype == torch.float32 else torch.bfloat16
+    dA, dB, ds = K.clip_bwd(A.cuda(), Bm.cuda(), s.cuda(), off, rm.cuda(), cm.cuda(), *w, g.cuda(), True, True, gd)
+    dAm, dBm, dsm = MK.clip_bwd(A, Bm, s, off, rm, cm, *w, g, True, True, torch.float64)
+    gtol = 1e-5 if (impl == 1 and dtype == torch.float32) else 2e-2
+    assert rel_err(dA, dAm) < gtol
+    assert rel_err(dB, dBm) < gtol
+    assert abs(float(ds) - float(dsm)) <= 1e-3 * abs(float(dsm)) + 2e-5     # cancelling sum, |dS| sums to ~2g
+    # partial-gradient weights (local_loss without gather_with_grad): w_col = 0 with +inf column LSEs
+    never = torch.full((N,), float("inf"))
+    dA2, _, _ = K.clip_bwd(A.cuda(), Bm.cuda(), s.cuda(), off, rm.cuda(), never.cuda(), 0.5 / M, 0.0, 0.5 / M,
+                           g.cuda(), True, False, gd)
+    dA2m, _, _ = MK.clip_bwd(A, Bm, s, off, rm, never, 0.5 / M, 0.0, 0.5 / M, g, True, False, torch.float64)
+    assert rel_err(dA2, dA2m) < gtol and torch.isfinite(dA2.float()).all()
+
+
+def test_clip_wide_dynamic_range(MK):
+    """Adversarial range for the online log-sum-exp: identical pairs at scale 100 next to near-orthogonal rows and
+    a few unnormalised rows -- logits span [-300, +400]."""
+    from xtag_clip_b200.kernels import CudaKernels
+    I, T = feats(5, 512, 256, corr=0.0, dtype=torch.bfloat16)
+    T[:256] = I[:256]                      # perfectly matched pairs: S_ii = 100
+    I[300:310] *= 4.0
+    T[400:405] *= -3.0
+    s = torch.tensor([100.0])
+    for impl in (1, 2):
+        K = CudaKernels(impl=impl)
+        row, col, diag = K.clip_fwd(I.cuda(), T.cuda(), s.cuda(), 0)
+        rm, cm, dm = MK.clip_fwd(I, T, s, 0)
+        assert torch.isfinite(row).all() and torch.isfinite(col).all()
+        assert rel_err(row, rm) < 2e-5 and rel_err(col, cm) < 2e-5 and rel_err(diag, dm) < 2e-5
+        dA, dB, ds = K.clip_bwd(I.cuda(), T.cuda(), s.cuda(), 0, rm.cuda(), cm.cuda(), 1 / 1024, 1 / 1024, 1 / 512,
+                                torch.tensor(1.0).cuda(), True, True, torch.float32)
+        dAm, dBm, dsm = MK.clip_bwd(I, T, s, 0, rm, cm, 1 / 1024, 1 / 1024, 1 / 512, torch.tensor(1.0), True, True,
+                                    torch.float64)
+        assert rel_err(dA, dAm) < 2e-2 and rel_err(dB, dBm) < 2e-2
+
+
+def test_lse_combine(K):
+    parts = torch.randn(5, 1000) * 30
+    parts[2, 10] = -float("inf")
+    out = K.lse_combine(parts.cuda())
+    assert rel_err(out, torch.logsumexp(parts.double(), 0)) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("b,Lq,Lk,heads,dh", [(3, 44, 50, 4, 192), (2, 44, 197, 4, 192), (2, 44, 257, 4, 192),
+                                              (2, 7, 5, 2, 16), (1, 44, 64, 4, 192)])
+def test_xattn(K, MK, dtype, b, Lq, Lk, heads, dh):
+    g = torch.Generator().manual_seed(b * 100 + Lk)
+    H = heads * dh
+    q = (torch.randn(b, Lq, H, generator=g) * 1.5).to(dtype)
+    kv = (torch.randn(b, Lk, 2 * H, generator=g) * 1.5).to(dtype)      # fused K|V projection buffer
+    k, v = kv[..., :H], kv[..., H:]
+    sc = 1 / math.sqrt(dh)
+    qc, kvc = q.cuda(), kv.cuda()
+    kc, vc = kvc[..., :H], kvc[..., H:]
+    o, lse = K.xattn_fwd(qc, kc, vc, heads, sc, 0.0, 0, 0)
+    om, lsem = MK.xattn_fwd(q, k, v, heads, sc, 0.0, 0, 0)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(o, om) < tol and rel_err(lse, lsem) < 1e-5 * (1 if dtype == torch.float32 else 100)
+    do = torch.randn(b, Lq, H, generator=g).to(dtype)
+    dq, dk, dv = K.xattn_bwd(qc, kc, vc, o, do.cuda(), lse, heads, sc, 0.0, 0, 0)
+    dqm, dkm, dvm = MK.xattn_bwd(q, k, v, om, do, lsem, heads, sc, 0.0, 0, 0)
+    assert rel_err(dq, dqm) < tol * 2 and rel_err(dk, dkm) < tol * 2 and rel_err(dv, dvm) < tol * 2
+
+
+def test_xattn_dropout(K):
+    """Dropout is keyed by (seed, offset): deterministic, rate ~ p, scaled by 1/(1-p), and the backward uses the
+    same mask (checked through the linearity of ctx in v)."""
+    b, Lq, Lk, heads, dh = 4, 44, 197, 4, 192
+    g = torch.Generator().manual_seed(1)
+    H = heads * dh
+    q = torch.zeros(b, Lq, H).cuda()                       # uniform attention: P = 1/Lk
+    k = torch.randn(b, Lk, H, generator=g).cuda()
+    v = torch.ones(b, Lk, H).cuda()
+    sc = 1 / math.sqrt(dh)
+    o1, _ = K.xattn_fwd(q, k, v, heads, sc, 0.1, 1234, 7)
+    o2, _ = K.xattn_fwd(q, k, v, heads, sc, 0.1, 1234, 7)
+    o3, _ = K.xattn_fwd(q, k, v, heads, sc, 0.1, 1234, 8)
+    assert torch.equal(o1, o2) and not torch.equal(o1, o3)
+    # each output = (#kept / Lk) / 0.9 ; mean over everything ~ 1
+    assert abs(o1.mean().item() - 1.0) < 5e-3
+    kept = o1[..., 0] * 0.9 * Lk                            # per (b, q, head 0) kept count
+    assert 0.85 < (kept / Lk).mean().item() < 0.95
+    # backward: dv[n] = sum_q Pdrop[q, n] * do[q]; with do = 1 the column sums of Pdrop come back
+    o, lse = K.xattn_fwd(q, k, v, heads, sc, 0.1, 99, 3)
+    do = torch.ones_like(o)
+    dq, dk, dv = K.xattn_bwd(q, k, v, o, do, lse, heads, sc, 0.1, 99, 3)
+    assert abs(dv[..., 0].sum(1).mean().item() - o[..., 0].sum(1).mean().item()) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- K5
+def test_asl_golden(K, golden_dir):
+    g = np.load(os.path.join(golden_dir, "asl.npz"))
+    x = torch.from_numpy(g["x"]).float().cuda()
+    y = torch.from_numpy(g["y"]).float().cuda()
+    for n in range(3):
+        gn, gp, clip = g[f"k{n}_cfg"]
+        loss, dx, idx = K.asl(x, y, gn, gp, clip, 1e-8, True, True)
+        assert rel_err(loss, g[f"k{n}_loss"]) < 1e-5
+        assert rel_err(dx, g[f"k{n}_dx"]) < 1e-5
+        ref_idx = oracle.control_word_indices(torch.from_numpy(g["x"]))
+        assert torch.equal(idx.cpu().long(), ref_idx)

@@ -20,6 +20,8 @@ SIGNATURES = {
     "xtag_last_error": (c_char_p, []),
     "xtag_device_check": (c_int, []),
     "xtag_launch_count": (c_uint64, []),
+    "xtag_prof_enable": (c_int, [c_int]),
+    "xtag_prof_read": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "xtag_l2norm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "xtag_l2norm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                 c_void_p]),

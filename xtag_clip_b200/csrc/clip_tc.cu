@@ -469,7 +469,10 @@ static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, in
   const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   int grid = num_sms();
   if (grid > num_tiles) grid = num_tiles;
-  tc_gemm_kernel<EPI><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, M, N, K, ep);
+  {
+    ProfScope prof(EPI, 2.0 * (double)M * (double)N * (double)K, st);
+    tc_gemm_kernel<EPI><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, M, N, K, ep);
+  }
   XTAG_CHECK_LAUNCH();
   return XTAG_OK;
 }

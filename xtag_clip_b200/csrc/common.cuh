@@ -47,6 +47,14 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
 
 int num_sms();
 
+// opt-in per-launch timing (CUDA events on the launching stream), see xtag_prof_enable in the header
+struct ProfScope {
+  int idx;
+  cudaStream_t st;
+  ProfScope(int tag, double work, cudaStream_t s);
+  ~ProfScope();
+};
+
 // ---- small device helpers ---------------------------------------------------------------------
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;

@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace xtag {
@@ -29,9 +32,63 @@ int num_sms() {
   return cached;
 }
 
+struct ProfRec {
+  int tag;
+  double work;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(int tag, double work, cudaStream_t s) : idx(-1), st(s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.tag = tag;
+  r.work = work;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, s);
+  g_prof.push_back(r);
+  idx = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].e1, st);
+}
+
 }  // namespace xtag
 
 extern "C" {
+
+int xtag_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(xtag::g_prof_mu);
+  for (auto& r : xtag::g_prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  xtag::g_prof.clear();
+  xtag::g_prof_on = on != 0;
+  return XTAG_OK;
+}
+
+int xtag_prof_read(int* tags, float* ms, double* work, int cap) {
+  std::lock_guard<std::mutex> lk(xtag::g_prof_mu);
+  int n = 0;
+  for (auto& r : xtag::g_prof) {
+    if (n >= cap) break;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) break;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) break;
+    tags[n] = r.tag;
+    ms[n] = t;
+    work[n] = r.work;
+    ++n;
+  }
+  return n;
+}
+
 
 int xtag_version(void) { return XTAG_ABI_VERSION; }
 
