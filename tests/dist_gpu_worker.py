@@ -1,0 +1,75 @@
+"""Multi-GPU parity worker (launched by tests/test_gpu_dist.py or by hand):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 \
+        tests/dist_gpu_worker.py
+
+One process per GPU over NCCL.  Every rank runs xtag_clip_b200.ClipLoss in all four local_loss x gather_with_grad
+modes on CUDA and checks its own loss / gradients against the single-process emulation of the reference's
+per-rank results (oracle.clip_loss_world, pinned to the reference under gloo by tests/test_oracle_golden.py)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+import oracle  # noqa: E402
+import xtag_clip_b200 as xt  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    failures = []
+    for (b, D, scale, dtype, ltol, gtol) in [(48, 64, 14.285714, torch.float32, 1e-5, 1e-5),
+                                             (256, 256, 30.0, torch.bfloat16, 1e-3, 2e-2),
+                                             (1024, 512, 14.285714, torch.bfloat16, 1e-3, 2e-2)]:
+        g = torch.Generator().manual_seed(100 + b)
+        I_all = torch.nn.functional.normalize(torch.randn(b * world, D, generator=g), dim=-1)
+        T_all = torch.nn.functional.normalize(0.3 * I_all + 0.7 * torch.randn(b * world, D, generator=g), dim=-1)
+        I_all, T_all = I_all.to(dtype), T_all.to(dtype)
+        Il = [I_all[r * b:(r + 1) * b].double() for r in range(world)]
+        Tl = [T_all[r * b:(r + 1) * b].double() for r in range(world)]
+        for ll in (False, True):
+            for gwg in (False, True):
+                losses, dI, dT, ds = oracle.clip_loss_world(Il, Tl, scale, ll, gwg)
+                I = I_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+                T = T_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+                s = torch.tensor(scale, device=dev, requires_grad=True)
+                mod = xt.ClipLoss(local_loss=ll, gather_with_grad=gwg, cache_labels=True, rank=rank, world_size=world)
+                loss = mod(I, T, s)
+                loss.backward()
+                tag = f"b={b} D={D} {dtype} ll={ll} gwg={gwg} rank={rank}"
+                e = (rel(loss, losses[rank]), rel(I.grad, dI[rank]), rel(T.grad, dT[rank]))
+                if e[0] > ltol or e[1] > gtol or e[2] > gtol:
+                    failures.append(f"{tag}: loss {e[0]:.2e} dI {e[1]:.2e} dT {e[2]:.2e}")
+                # d(logit_scale): compare what DDP would reduce (sum over ranks)
+                tot = s.grad.detach().clone()
+                dist.all_reduce(tot)
+                ref_tot = float(sum(ds))
+                if abs(tot.item() - ref_tot) > 2e-2 * abs(ref_tot) + 5e-5:
+                    failures.append(f"{tag}: dscale sum {tot.item():.6e} vs {ref_tot:.6e}")
+    n_fail = torch.tensor([len(failures)], device=dev)
+    dist.all_reduce(n_fail)
+    for f in failures:
+        print("FAIL", f, flush=True)
+    if rank == 0:
+        print(f"dist_gpu_worker: world={world} total_failures={int(n_fail)}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(1 if int(n_fail) else 0)
+
+
+if __name__ == "__main__":
+    main()
