@@ -118,6 +118,11 @@ int xtag_clip_bwd(const void* A, const void* Bm, int dtype, int M, int N, int D,
  *   C[M,N] = alpha * A[M,K] * B[N,K]^T   (A, B bf16 row-major "K-major"; C f32 or bf16; alpha by value) */
 int xtag_tc_gemm_nt(const void* A, const void* B, void* C, int c_dtype,
                     int M, int N, int K, float alpha, void* stream);
+/* general operand layouts: C[M,N] = alpha * sum_k A(m,k) B(n,k); a_mn = 0: A stored [M][K], 1: stored [K][M]
+ * ("MN-major", read in place through an MN-major UMMA descriptor); b_mn likewise with N.  (a_mn, b_mn) in
+ * {(0,0), (0,1), (1,1)}: the three layouts K2 uses (S = A Bm^T, dA = dS Bm, dB = dS^T A). */
+int xtag_tc_gemm(const void* A, const void* B, void* C, int c_dtype,
+                 int M, int N, int K, float alpha, int a_mn, int b_mn, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  tag-head cross-attention core.  Replaces the eager attention in

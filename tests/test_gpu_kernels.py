@@ -90,6 +90,23 @@ def test_tc_gemm_nt(K, M, N, Kd):
     assert rel_err(Cb, ref) < 6e-3
 
 
+@pytest.mark.parametrize("M,N,Kd", [(128, 256, 64), (256, 512, 128), (200, 304, 72), (64, 1024, 4096), (4096, 1024, 4096),
+                                    (1024, 512, 1000)])
+def test_tc_gemm_mn_major_operands(K, M, N, Kd):
+    """The operand layouts of the two gradient GEMMs: B read in place as [K][N] (dA = dS Bm), and both A and B read
+    in place as [K][M] / [K][N] (dB = dS^T A): MN-major UMMA descriptors over 64-wide TMA boxes."""
+    g = torch.Generator().manual_seed(M * 3 + N + Kd)
+    A = torch.randn(M, Kd, generator=g).bfloat16().cuda()
+    Bkn = torch.randn(Kd, N, generator=g).bfloat16().cuda()
+    ref = A.float() @ Bkn.float()
+    C = K.tc_gemm(A, Bkn, False, True, torch.float32)
+    assert rel_err(C, ref) < 2e-5
+    if M % 8 == 0:
+        Akm = A.T.contiguous()
+        C2 = K.tc_gemm(Akm, Bkn, True, True, torch.float32)
+        assert rel_err(C2, ref) < 2e-5
+
+
 # ---------------------------------------------------------------------------------------------- K1 / K2 kernels
 SHAPES = [(16, 16, 32, 0), (64, 64, 64, 0), (33, 47, 40, 5), (130, 300, 72, 100), (256, 256, 512, 0),
           (128, 1024, 512, 384), (1024, 1024, 512, 0)]

@@ -35,6 +35,7 @@ SIGNATURES = {
                               c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
                               c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "xtag_tc_gemm_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "xtag_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "xtag_xattn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_float, c_float, c_uint64, c_uint64, c_void_p]),

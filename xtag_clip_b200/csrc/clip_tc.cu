@@ -96,7 +96,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int EPI>
+// A_MN / B_MN: the operand is stored "MN-major": global tensor [K rows][M or N contiguous] (e.g. dS read as the
+// A operand of dB = dS^T A, or row-major features read as the B operand [N=D][K] of dA = dS Bm).  TMA then loads
+// 64-element (128 B) wide boxes of BK rows; UMMA reads them through an MN-major 128B-swizzle descriptor.
+template <int EPI, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, EpiParams ep) {
@@ -154,8 +157,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_arrive_expect_tx(fb, kStageBytes);
           const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-          tma_load_2d(sa, &tmA, fb, kb * BK, m_blk * BM);
-          tma_load_2d(sa + kABytes, &tmB, fb, kb * BK, n_blk * BN);
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int u = 0; u < BM / 64; ++u)
+              tma_load_2d(sa + u * (BK * 128), &tmA, fb, m_blk * BM + u * 64, kb * BK);
+          } else {
+            tma_load_2d(sa, &tmA, fb, kb * BK, m_blk * BM);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int u = 0; u < BN / 64; ++u)
+              tma_load_2d(sa + kABytes + u * (BK * 128), &tmB, fb, n_blk * BN + u * 64, kb * BK);
+          } else {
+            tma_load_2d(sa + kABytes, &tmB, fb, kb * BK, n_blk * BN);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -163,8 +178,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN, 0, 0);
-      constexpr uint64_t desc_hi = make_smem_desc_hi(16, 1024, kSwizzle128B);   // K-major, 128B swizzle
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      // K-major : rows of 64 K-elements (128 B), 8-row swizzle atoms 1024 B apart (SBO); LBO unused
+      // MN-major: 64 MN-elements per 128 B row, one row per K index; 8 K-rows = one 1024 B atom (SBO),
+      //           the next 64 MN-elements live in the next TMA box, BK*128 B further (LBO)
+      constexpr uint64_t desc_hi_k = make_smem_desc_hi(16, 1024, kSwizzle128B);
+      constexpr uint64_t desc_hi_mn = make_smem_desc_hi(BK * 128, 1024, kSwizzle128B);
+      constexpr uint64_t a_hi = A_MN ? desc_hi_mn : desc_hi_k;
+      constexpr uint64_t b_hi = B_MN ? desc_hi_mn : desc_hi_k;
+      // descriptor start-address step per 16-wide K slice (encoded >> 4): 32 B inside a K-major swizzle row,
+      // 16 rows * 128 B for MN-major
+      constexpr uint64_t a_step = A_MN ? (16 * 128) >> 4 : 2;
+      constexpr uint64_t b_step = B_MN ? (16 * 128) >> 4 : 2;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -177,13 +202,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-          const uint64_t da = make_smem_desc(sa, desc_hi);
-          const uint64_t db = make_smem_desc(sa + kABytes, desc_hi);
+          const uint64_t da = make_smem_desc(sa, a_hi);
+          const uint64_t db = make_smem_desc(sa + kABytes, b_hi);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 bytes per 16-element K step inside the 128-byte swizzle row (encoded >> 4)
-            umma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, da + (uint64_t)k * a_step, db + (uint64_t)k * b_step, idesc, (uint32_t)((kb | k) != 0));
           umma_commit(smem_u32(&empty_bar[stage]));       // frees the smem slot when the MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -231,24 +254,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_32x32(taddr + ch * 32, r);
           tmem_ld_wait();
           const int c0 = n_base + ch * 32;
-          float v[32], x[32];
-          float cm = -INFINITY;
+          float v[32];
+          float cm = -INFINITY, vmin = INFINITY;
+          if (c0 + 32 <= N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const bool col_ok = (c0 + j) < N;
-            const float s = __uint_as_float(r[j]) * sl2;
-            v[j] = col_ok ? s : -INFINITY;
-            cm = fmaxf(cm, v[j]);
-            x[j] = row_ok ? v[j] : -INFINITY;
-          }
-          // ---- row statistics (thread local, online) ----
-          if (cm > -INFINITY) {
-            const float m_new = fmaxf(m_run, cm);
-            float sum = 0.f;
+            for (int j = 0; j < 32; ++j) {
+              v[j] = __uint_as_float(r[j]) * sl2;
+              cm = fmaxf(cm, v[j]);
+              vmin = fminf(vmin, v[j]);
+            }
+          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sum += fast_exp2(v[j] - m_new);
-            l_run = l_run * fast_exp2(m_run - m_new) + sum;
-            m_run = m_new;
+            for (int j = 0; j < 32; ++j) {
+              const bool col_ok = (c0 + j) < N;
+              const float s = __uint_as_float(r[j]) * sl2;
+              v[j] = col_ok ? s : -INFINITY;
+              cm = fmaxf(cm, v[j]);
+              vmin = col_ok ? fminf(vmin, s) : vmin;
+            }
           }
           if (row_ok && lab >= c0 && lab < c0 + 32) {
             float dv = 0.f;
@@ -256,27 +279,60 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) dv = (lab - c0 == j) ? v[j] : dv;
             ep.diag[gi] = dv * kLn2;
           }
-          // ---- column statistics over this warp's 32 rows (exact: per-column max, then sum) ----
-          warp_transpose_reduce<true>(x, lane);                 // x[0] = max of column `lane`
-          float* cmax_s = scratch + q * 128 + ch * 32;          // reuse the output slot as staging
-          cmax_s[lane] = x[0];
-          __syncwarp();
-          float ex[32];
+          // ---- one exponential per element, referenced to this row's chunk maximum ----
+          //   row   : sum_j 2^(v_ij - cm_i), folded into the running (max, sum) with two scalar exps
+          //   column: 2^(v_ij - W) = e_ij * 2^(cm_i - W) with W = max of cm over the warp's 32 rows, so the same
+          //           exponentials serve the column sums.  Exact unless an element lies more than 2^-kRange below
+          //           W (it would flush to zero while possibly dominating its own column): such chunks -- only
+          //           ever seen when a 32x32 block spans > 83 nats -- take the exact two-exp path below.
+          constexpr float kRange = 120.f;
+          float e[32];
+          float rsum = 0.f;
+          const float cm_safe = (cm > -INFINITY) ? cm : 0.f;
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 c4 = *reinterpret_cast<const float4*>(cmax_s + j4 * 4);
-            const float cmx[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int j = j4 * 4 + u;
-              // column with no valid entry: max = -inf -> contributes nothing
-              ex[j] = (row_ok && cmx[u] > -INFINITY) ? fast_exp2(v[j] - cmx[u]) : 0.f;
-            }
+          for (int j = 0; j < 32; ++j) {
+            e[j] = fast_exp2(v[j] - cm_safe);
+            rsum += e[j];
           }
-          __syncwarp();
-          const float my_cmax = x[0];
-          warp_transpose_reduce<false>(ex, lane);               // ex[0] = sum of column `lane`
-          cmax_s[lane] = (ex[0] > 0.f) ? my_cmax + fast_log2(ex[0]) : -INFINITY;
+          if (cm > -INFINITY) {
+            const float m_new = fmaxf(m_run, cm);
+            l_run = l_run * fast_exp2(m_run - m_new) + rsum * fast_exp2(cm - m_new);
+            m_run = m_new;
+          }
+          const float W = warp_max(row_ok ? cm : -INFINITY);
+          const float lo = -warp_max(row_ok ? -vmin : -INFINITY);
+          float* cslot = scratch + q * 128 + ch * 32;
+          if (W - lo <= kRange) {
+            // fast path (warp-uniform branch)
+            const float f = (row_ok && cm > -INFINITY) ? fast_exp2(cm - W) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) e[j] *= f;
+            warp_transpose_reduce<false>(e, lane);              // e[0] = sum over rows of column `lane`
+            cslot[lane] = (e[0] > 0.f) ? W + fast_log2(e[0]) : -INFINITY;
+          } else {
+            // exact path: per-column maximum, then a second exponential
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = row_ok ? v[j] : -INFINITY;
+            warp_transpose_reduce<true>(x, lane);               // x[0] = max of column `lane`
+            cslot[lane] = x[0];
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 c4 = *reinterpret_cast<const float4*>(cslot + j4 * 4);
+              const float cmx[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int j = j4 * 4 + u;
+                // column with no valid entry: max = -inf -> contributes nothing
+                e[j] = (row_ok && cmx[u] > -INFINITY) ? fast_exp2(v[j] - cmx[u]) : 0.f;
+              }
+            }
+            __syncwarp();
+            const float my_cmax = x[0];
+            warp_transpose_reduce<false>(e, lane);
+            cslot[lane] = (e[0] > 0.f) ? my_cmax + fast_log2(e[0]) : -INFINITY;
+          }
         }
         // row partial for this (n tile, half)
         if (row_ok)
@@ -436,15 +492,15 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// bf16 row-major [rows, cols] matrix with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle
-static int make_tmap_bf16(CUtensorMap* tm, const void* base, int rows, int cols, long ld, int box_rows) {
+// bf16 row-major [outer, inner] matrix with row stride ld (elements); TMA box = [box_outer rows, 64 inner], 128B swizzle
+static int make_tmap_bf16(CUtensorMap* tm, const void* base, int outer, int inner, long ld, int box_outer) {
   PFN_encodeTiled enc = get_encode();
   XTAG_REQUIRE(enc != nullptr, XTAG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   XTAG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, XTAG_ERR_UNSUPPORTED,
                "TMA operand must be 16-byte aligned with a 16-byte multiple row stride (ld=%ld)", ld);
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -453,17 +509,20 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, int rows, int cols,
   return XTAG_OK;
 }
 
-template <int EPI>
+// acc[M,N] = sum_k A(m,k) B(n,k).  K-major operand: memory [M|N rows][K], row stride ld.
+//                                   MN-major operand: memory [K rows][M|N], row stride ld.
+template <int EPI, bool A_MN, bool B_MN>
 static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiParams& ep,
                      cudaStream_t st) {
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16(&tmA, A, M, K, lda, BM);
+  int rc = A_MN ? make_tmap_bf16(&tmA, A, K, M, lda, BK) : make_tmap_bf16(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tmB, B, N, K, ldb, BN);
+  rc = B_MN ? make_tmap_bf16(&tmB, B, K, N, ldb, BK) : make_tmap_bf16(&tmB, B, N, K, ldb, BN);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    XTAG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    XTAG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kSmemBytes));
     attr_set = true;
   }
   const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
@@ -471,7 +530,7 @@ static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, in
   if (grid > num_tiles) grid = num_tiles;
   {
     ProfScope prof(EPI, 2.0 * (double)M * (double)N * (double)K, st);
-    tc_gemm_kernel<EPI><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, M, N, K, ep);
+    tc_gemm_kernel<EPI, A_MN, B_MN><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, M, N, K, ep);
   }
   XTAG_CHECK_LAUNCH();
   return XTAG_OK;
@@ -505,26 +564,37 @@ int tc_clip_fwd(const void* A, const void* Bm, int M, int N, int D, const float*
   ep.row_part = (float*)ws;
   ep.col_part = (float*)((uint8_t*)ws + align256(2 * (size_t)num_n * M * 4));
   ep.diag = diag;
-  int rc = launch_tc<EPI_LSE>(A, D, Bm, D, M, N, D, ep, st);
+  int rc = launch_tc<EPI_LSE, false, false>(A, D, Bm, D, M, N, D, ep, st);
   if (rc) return rc;
   rc = launch_lse_reduce(ep.row_part, 2 * num_n, M, 1.f, kLn2, row_lse, st);
   if (rc) return rc;
   return launch_lse_reduce(ep.col_part, num_m, N, 1.f, kLn2, col_lse, st);
 }
 
-// workspace: dS [M][Np] bf16, dS^T [N][Mp] bf16, A^T [D][Mp] bf16, Bm^T [D][Np] bf16, dscale partials
+// Backward workspace.  Default ("mn") layout: dS [M][Np] bf16 only -- the two gradient GEMMs read dS and the
+// features in place through MN-major UMMA descriptors.  XTAG_TC_BWD_LAYOUT=transposed (A/B testing only) also
+// stages dS^T [N][Mp] and transposed features so that every operand is K-major.
 struct BwdLayout {
   size_t Mp, Np, off_ds, off_dst, off_at, off_bt, off_part, total;
 };
+static bool bwd_transposed_layout() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("XTAG_TC_BWD_LAYOUT");
+    cached = (e && e[0] == 't') ? 1 : 0;
+  }
+  return cached == 1;
+}
 static BwdLayout bwd_layout(int M, int N, int D) {
   BwdLayout L;
+  const bool tr = bwd_transposed_layout();
   L.Mp = ((size_t)M + 7) & ~(size_t)7;
   L.Np = ((size_t)N + 7) & ~(size_t)7;
   size_t o = 0;
   L.off_ds = o;   o += align256((size_t)M * L.Np * 2);
-  L.off_dst = o;  o += align256((size_t)N * L.Mp * 2);
-  L.off_at = o;   o += align256((size_t)D * L.Mp * 2);
-  L.off_bt = o;   o += align256((size_t)D * L.Np * 2);
+  L.off_dst = o;  o += tr ? align256((size_t)N * L.Mp * 2) : 0;
+  L.off_at = o;   o += tr ? align256((size_t)D * L.Mp * 2) : 0;
+  L.off_bt = o;   o += tr ? align256((size_t)D * L.Np * 2) : 0;
   L.off_part = o; o += align256((size_t)256 * kEpiWarps * 4);
   L.total = o + 256;
   return L;
@@ -556,6 +626,7 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
                 const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
                 void* ws, size_t ws_bytes, cudaStream_t st) {
   const BwdLayout L = bwd_layout(M, N, D);
+  const bool tr = bwd_transposed_layout();
   XTAG_REQUIRE(ws && ws_bytes >= L.total, XTAG_ERR_WORKSPACE, "clip_bwd(tc): workspace %zu < %zu", ws_bytes, L.total);
   uint8_t* w = (uint8_t*)ws;
   __nv_bfloat16* dS = (__nv_bfloat16*)(w + L.off_ds);
@@ -564,9 +635,9 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
   __nv_bfloat16* Bt = (__nv_bfloat16*)(w + L.off_bt);
   float* part = (float*)(w + L.off_part);
 
-  // padding columns of dS / dS^T must be zero when M or N is not a multiple of 8 (they enter the K sums)
+  // padding columns of dS (N not a multiple of 8) enter the K sum of dA: keep them zero
   if (L.Np != (size_t)N) XTAG_CUDA(cudaMemsetAsync(dS, 0, (size_t)M * L.Np * 2, st));
-  if (dB && L.Mp != (size_t)M) XTAG_CUDA(cudaMemsetAsync(dST, 0, (size_t)N * L.Mp * 2, st));
+  if (tr && dB && L.Mp != (size_t)M) XTAG_CUDA(cudaMemsetAsync(dST, 0, (size_t)N * L.Mp * 2, st));
 
   EpiParams ep = {};
   ep.scale_p = scale;
@@ -576,33 +647,43 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
   ep.w_row = w_row; ep.w_col = w_col; ep.w_diag = w_diag;
   ep.grad_out = grad_out;
   ep.dS = dS; ep.ldds = (int)L.Np;
-  ep.dST = dB ? dST : nullptr; ep.lddst = (int)L.Mp;
+  ep.dST = (tr && dB) ? dST : nullptr; ep.lddst = (int)L.Mp;
   ep.dscale_part = part;
   const int grid = tc_grid_for(M, N);
-  int rc = launch_tc<EPI_DS>(A, D, Bm, D, M, N, D, ep, st);
+  int rc = launch_tc<EPI_DS, false, false>(A, D, Bm, D, M, N, D, ep, st);
   if (rc) return rc;
   if (dscale) {
     rc = launch_sum_into(part, grid * kEpiWarps, dscale, st);
     if (rc) return rc;
   }
+  EpiParams es = {};
+  es.ldc = D; es.c_is_bf16 = (grad_dtype == XTAG_BF16); es.alpha = 1.f; es.alpha_p = scale;
   if (dA) {
-    // dA[M,D] = scale * dS[M,N] * Bm[N,D]  ==  dS (K-major over j)  x  (Bm^T)[D,N] (K-major over j)
-    dim3 g((D + 31) / 32, (N + 31) / 32);
-    transpose_pad_bf16_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)Bm, Bt, N, D, (int)L.Np);
-    XTAG_CHECK_LAUNCH();
-    EpiParams es = {};
-    es.C = dA; es.ldc = D; es.c_is_bf16 = (grad_dtype == XTAG_BF16); es.alpha = 1.f; es.alpha_p = scale;
-    rc = launch_tc<EPI_STORE>(dS, (long)L.Np, Bt, (long)L.Np, M, D, N, es, st);
+    es.C = dA;
+    if (!tr) {
+      // dA[i,d] = s * sum_j dS[i,j] Bm[j,d]: A operand dS is K-major (j contiguous); B operand (n=d, k=j) is the
+      // feature matrix itself, [K=j rows][N=d contiguous] = MN-major
+      rc = launch_tc<EPI_STORE, false, true>(dS, (long)L.Np, Bm, (long)D, M, D, N, es, st);
+    } else {
+      dim3 g((D + 31) / 32, (N + 31) / 32);
+      transpose_pad_bf16_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)Bm, Bt, N, D, (int)L.Np);
+      XTAG_CHECK_LAUNCH();
+      rc = launch_tc<EPI_STORE, false, false>(dS, (long)L.Np, Bt, (long)L.Np, M, D, N, es, st);
+    }
     if (rc) return rc;
   }
   if (dB) {
-    // dB[N,D] = scale * dS^T[N,M] * A[M,D]  ==  dS^T (K-major over i)  x  (A^T)[D,M] (K-major over i)
-    dim3 g((D + 31) / 32, (M + 31) / 32);
-    transpose_pad_bf16_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)A, At, M, D, (int)L.Mp);
-    XTAG_CHECK_LAUNCH();
-    EpiParams es = {};
-    es.C = dB; es.ldc = D; es.c_is_bf16 = (grad_dtype == XTAG_BF16); es.alpha = 1.f; es.alpha_p = scale;
-    rc = launch_tc<EPI_STORE>(dST, (long)L.Mp, At, (long)L.Mp, N, D, M, es, st);
+    es.C = dB;
+    if (!tr) {
+      // dB[j,d] = s * sum_i dS[i,j] A[i,d]: A operand (m=j, k=i) is dS read as [K=i rows][M=j contiguous];
+      // B operand (n=d, k=i) is A read as [K=i rows][N=d contiguous]: both MN-major, nothing is transposed
+      rc = launch_tc<EPI_STORE, true, true>(dS, (long)L.Np, A, (long)D, N, D, M, es, st);
+    } else {
+      dim3 g((D + 31) / 32, (M + 31) / 32);
+      transpose_pad_bf16_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)A, At, M, D, (int)L.Mp);
+      XTAG_CHECK_LAUNCH();
+      rc = launch_tc<EPI_STORE, false, false>(dST, (long)L.Mp, At, (long)L.Mp, N, D, M, es, st);
+    }
     if (rc) return rc;
   }
   return XTAG_OK;
@@ -612,14 +693,28 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
 
 using namespace xtag;
 
-extern "C" int xtag_tc_gemm_nt(const void* A, const void* B, void* C, int c_dtype, int M, int N, int K, float alpha,
-                               void* stream) {
-  XTAG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, XTAG_ERR_INVALID, "tc_gemm_nt: bad arguments");
-  XTAG_REQUIRE(K % 8 == 0, XTAG_ERR_UNSUPPORTED, "tc_gemm_nt: K must be a multiple of 8 (16-byte TMA rows)");
-  XTAG_REQUIRE(c_dtype == XTAG_F32 || c_dtype == XTAG_BF16, XTAG_ERR_INVALID, "tc_gemm_nt: bad C dtype");
+// C[M,N] = alpha * sum_k A(m,k) B(n,k).  a_mn == 0: A is [M][K] row-major, a_mn == 1: A is [K][M] row-major;
+// same for B with N.  Contiguous operands (leading dimension = inner extent).
+extern "C" int xtag_tc_gemm(const void* A, const void* B, void* C, int c_dtype, int M, int N, int K, float alpha,
+                            int a_mn, int b_mn, void* stream) {
+  XTAG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, XTAG_ERR_INVALID, "tc_gemm: bad arguments");
+  XTAG_REQUIRE((a_mn ? M : K) % 8 == 0 && (b_mn ? N : K) % 8 == 0, XTAG_ERR_UNSUPPORTED,
+               "tc_gemm: the contiguous extent of each operand must be a multiple of 8 (16-byte TMA rows)");
+  XTAG_REQUIRE(c_dtype == XTAG_F32 || c_dtype == XTAG_BF16, XTAG_ERR_INVALID, "tc_gemm: bad C dtype");
   int rc = xtag_device_check();
   if (rc) return rc;
   EpiParams es = {};
   es.C = C; es.ldc = N; es.c_is_bf16 = (c_dtype == XTAG_BF16); es.alpha = alpha; es.alpha_p = nullptr;
-  return launch_tc<EPI_STORE>(A, K, B, K, M, N, K, es, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long lda = a_mn ? M : K, ldb = b_mn ? N : K;
+  if (!a_mn && !b_mn) return launch_tc<EPI_STORE, false, false>(A, lda, B, ldb, M, N, K, es, st);
+  if (!a_mn && b_mn) return launch_tc<EPI_STORE, false, true>(A, lda, B, ldb, M, N, K, es, st);
+  if (a_mn && b_mn) return launch_tc<EPI_STORE, true, true>(A, lda, B, ldb, M, N, K, es, st);
+  set_error("tc_gemm: A MN-major with B K-major is not instantiated");
+  return XTAG_ERR_UNSUPPORTED;
+}
+
+extern "C" int xtag_tc_gemm_nt(const void* A, const void* B, void* C, int c_dtype, int M, int N, int K, float alpha,
+                               void* stream) {
+  return xtag_tc_gemm(A, B, C, c_dtype, M, N, K, alpha, 0, 0, stream);
 }

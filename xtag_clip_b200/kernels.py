@@ -142,6 +142,18 @@ class CudaKernels:
               "xtag_tc_gemm_nt")
         return C
 
+    def tc_gemm(self, A: torch.Tensor, B: torch.Tensor, a_mn: bool, b_mn: bool, out_dtype=torch.float32,
+                alpha: float = 1.0):
+        """C[M,N] = alpha * sum_k A(m,k) B(n,k); A is [M,K] (a_mn False) or [K,M] (True), B is [N,K] or [K,N]."""
+        _cuda(A, B)
+        A, B = A.contiguous(), B.contiguous()
+        (K, M) = A.shape if a_mn else A.shape[::-1]
+        N = B.shape[1] if b_mn else B.shape[0]
+        C = torch.empty((M, N), dtype=out_dtype, device=A.device)
+        check(self.lib.xtag_tc_gemm(_p(A), _p(B), _p(C), _DT[out_dtype], M, N, K, float(alpha), int(a_mn), int(b_mn),
+                                    _stream()), "xtag_tc_gemm")
+        return C
+
     # ---- K4 ----------------------------------------------------------------------------------
     def xattn_fwd(self, q, k, v, heads: int, softmax_scale: float, dropout_p: float, seed: int, offset: int):
         """q [b,Lq,H], k/v [b,Lk,H] (last dim contiguous; k and v may be strided views of one buffer)
