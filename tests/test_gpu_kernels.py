@@ -211,29 +211,31 @@ def test_xattn(K, MK, dtype, b, Lq, Lk, heads, dh):
     assert rel_err(dq, dqm) < tol * 2 and rel_err(dk, dkm) < tol * 2 and rel_err(dv, dvm) < tol * 2
 
 
-def test_xattn_dropout(K):
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_xattn_dropout(K, dtype):
     """Dropout is keyed by (seed, offset): deterministic, rate ~ p, scaled by 1/(1-p), and the backward uses the
-    same mask (checked through the linearity of ctx in v)."""
+    same mask (checked through the linearity of ctx in v).  bf16 exercises the mma/TMA forward kernel."""
     b, Lq, Lk, heads, dh = 4, 44, 197, 4, 192
     g = torch.Generator().manual_seed(1)
     H = heads * dh
-    q = torch.zeros(b, Lq, H).cuda()                       # uniform attention: P = 1/Lk
-    k = torch.randn(b, Lk, H, generator=g).cuda()
-    v = torch.ones(b, Lk, H).cuda()
+    q = torch.zeros(b, Lq, H).to(dtype).cuda()             # uniform attention: P = 1/Lk
+    k = torch.randn(b, Lk, H, generator=g).to(dtype).cuda()
+    v = torch.ones(b, Lk, H).to(dtype).cuda()
     sc = 1 / math.sqrt(dh)
     o1, _ = K.xattn_fwd(q, k, v, heads, sc, 0.1, 1234, 7)
     o2, _ = K.xattn_fwd(q, k, v, heads, sc, 0.1, 1234, 7)
     o3, _ = K.xattn_fwd(q, k, v, heads, sc, 0.1, 1234, 8)
     assert torch.equal(o1, o2) and not torch.equal(o1, o3)
     # each output = (#kept / Lk) / 0.9 ; mean over everything ~ 1
-    assert abs(o1.mean().item() - 1.0) < 5e-3
-    kept = o1[..., 0] * 0.9 * Lk                            # per (b, q, head 0) kept count
+    assert abs(o1.float().mean().item() - 1.0) < 6e-3
+    kept = o1[..., 0].float() * 0.9 * Lk                    # per (b, q, head 0) kept count
     assert 0.85 < (kept / Lk).mean().item() < 0.95
     # backward: dv[n] = sum_q Pdrop[q, n] * do[q]; with do = 1 the column sums of Pdrop come back
     o, lse = K.xattn_fwd(q, k, v, heads, sc, 0.1, 99, 3)
     do = torch.ones_like(o)
     dq, dk, dv = K.xattn_bwd(q, k, v, o, do, lse, heads, sc, 0.1, 99, 3)
-    assert abs(dv[..., 0].sum(1).mean().item() - o[..., 0].sum(1).mean().item()) < 1e-3
+    assert abs(dv[..., 0].float().sum(1).mean().item() - o[..., 0].float().sum(1).mean().item()) < (
+        1e-3 if dtype == torch.float32 else 0.3)
 
 
 # ---------------------------------------------------------------------------------------------- K5

@@ -92,8 +92,261 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&x)[32], int lane) 
   }
 }
 
+// r[idx] for a per-thread idx in [0,32) as a 5-level select tree (31 selects, registers only: a dynamic
+// subscript would push the whole array to local memory)
+__device__ __forceinline__ float select32(const uint32_t (&r)[32], int idx) {
+  float t16[16], t8[8], t4[4], t2[2];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) t16[k] = __uint_as_float((idx & 16) ? r[k + 16] : r[k]);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t8[k] = (idx & 8) ? t16[k + 8] : t16[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t4[k] = (idx & 4) ? t8[k + 4] : t8[k];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) t2[k] = (idx & 2) ? t4[k + 2] : t4[k];
+  return (idx & 1) ? t2[1] : t2[0];
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue bodies.  One call handles this warp's 32 rows x 128 columns of a finished accumulator (4 chunks of
+// 32 columns read with tcgen05.ld 32x32b: thread = row).  FULL = no ragged edge inside the block, so every
+// bounds predicate folds away at compile time.
+// ---------------------------------------------------------------------------------------------------------
+
+// K1: log2-domain (max, sum-exp) partials per row and per column + label logit.
+//   one exponential per element, referenced to the row's chunk maximum cm_i:
+//     row   : sum_j 2^(v_ij - cm_i), folded into the running (max, sum) with two scalar exps per chunk
+//     column: 2^(v_ij - W) = e_ij * 2^(cm_i - W), W = max of cm over the warp's 32 rows -> the same exponentials
+//             serve the column sums after one multiply and a 31-shuffle transpose-reduce.
+//   Exact unless an element lies more than 2^-kRange below W (it would flush to zero while possibly dominating
+//   its own column): such chunks -- a 32x32 block spanning > 83 nats -- take the exact two-exp path.
+template <bool FULL>
+__device__ __forceinline__ void lse_tile(const EpiParams& ep, uint32_t taddr, float* scratch, int gi, int n_base,
+                                         int m_blk, int n_blk, int h, int q, int lane, int M, int N,
+                                         uint32_t tempty, int bar_id) {
+  constexpr float kRange = 120.f;
+  const float sl2 = ep.scale_p[0] * kLog2e;
+  const bool row_ok = FULL || gi < M;
+  const int lab = gi + ep.label_offset;
+  float m_run = -INFINITY, l_run = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + ch * 32, r);
+    tmem_ld_wait();
+    const int c0 = n_base + ch * 32;
+    // raw accumulators a_j = <A_i, B_j>; v_j = a_j * sl2.  max / min on the raw values in 4 interleaved chains
+    // (two epilogue warps per scheduler hide little latency); the scale is folded into the exponent FFMA.
+    float amx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    float amn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = __uint_as_float(r[j]);
+      if (FULL || (c0 + j) < N) {
+        amx[j & 3] = fmaxf(amx[j & 3], a);
+        amn[j & 3] = fminf(amn[j & 3], a);
+      }
+    }
+    const float amax = fmaxf(fmaxf(amx[0], amx[1]), fmaxf(amx[2], amx[3]));
+    const float amin = fminf(fminf(amn[0], amn[1]), fminf(amn[2], amn[3]));
+    const bool any_col = FULL || amax > -INFINITY;                // false only for a chunk entirely past N
+    const float cm = any_col ? ((sl2 >= 0.f) ? amax * sl2 : amin * sl2) : -INFINITY;
+    const float vmin = any_col ? ((sl2 >= 0.f) ? amin * sl2 : amax * sl2) : INFINITY;
+    if (row_ok && lab >= c0 && lab < c0 + 32) {
+      const float dv = select32(r, lab - c0);
+      // same rounding sequence as the row LSE ((a*sl2 + log2 l) * ln2): lse - diag cancels exactly for rows
+      // dominated by their label
+      ep.diag[gi] = (dv * sl2) * kLn2;
+    }
+    float ex[32];
+    float rsp[4] = {0.f, 0.f, 0.f, 0.f};
+    const float ncm = any_col ? -cm : 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float t = fast_exp2(fmaf(__uint_as_float(r[j]), sl2, ncm));
+      ex[j] = (FULL || (c0 + j) < N) ? t : 0.f;
+      rsp[j & 3] += ex[j];
+    }
+    const float rsum = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
+    if (any_col) {
+      const float m_new = fmaxf(m_run, cm);
+      l_run = l_run * fast_exp2(m_run - m_new) + rsum * fast_exp2(cm - m_new);
+      m_run = m_new;
+    }
+    const float W = warp_max(row_ok ? cm : -INFINITY);
+    const float lo = -warp_max(row_ok ? -vmin : -INFINITY);
+    float* cslot = scratch + q * 128 + ch * 32;
+    if (W - lo <= kRange) {
+      // fast path (warp-uniform branch)
+      const float f = (row_ok && any_col) ? fast_exp2(cm - W) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ex[j] *= f;
+      warp_transpose_reduce<false>(ex, lane);             // ex[0] = sum over rows of column `lane`
+      cslot[lane] = (ex[0] > 0.f) ? W + fast_log2(ex[0]) : -INFINITY;
+    } else {
+      // exact path: per-column maximum, then a second exponential
+      // (re-reads the chunk from TMEM so the fast path need not keep the raw accumulators alive)
+      float x[32], v[32];
+      uint32_t rr[32];
+      tmem_ld_32x32(taddr + ch * 32, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = (FULL || (c0 + j) < N) ? __uint_as_float(rr[j]) * sl2 : -INFINITY;
+        x[j] = row_ok ? v[j] : -INFINITY;
+      }
+      warp_transpose_reduce<true>(x, lane);               // x[0] = max of column `lane`
+      cslot[lane] = x[0];
+      __syncwarp();
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(cslot + j4 * 4);
+        const float cmx[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j4 * 4 + u;
+          // column with no valid entry: max = -inf -> contributes nothing
+          ex[j] = (row_ok && cmx[u] > -INFINITY) ? fast_exp2(v[j] - cmx[u]) : 0.f;
+        }
+      }
+      __syncwarp();
+      const float my_cmax = x[0];
+      warp_transpose_reduce<false>(ex, lane);
+      cslot[lane] = (ex[0] > 0.f) ? my_cmax + fast_log2(ex[0]) : -INFINITY;
+    }
+  }
+  // row partial for this (n tile, half)
+  if (row_ok) ep.row_part[(size_t)(n_blk * 2 + h) * M + gi] = (l_run > 0.f) ? m_run + fast_log2(l_run) : -INFINITY;
+  // TMEM reads of this warp are complete: release the accumulator before the cross-warp combine
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tempty);
+  named_bar_sync(bar_id, 128);
+  {
+    const int c = q * 32 + lane;
+    const float p0 = scratch[0 * 128 + c], p1 = scratch[1 * 128 + c];
+    const float p2 = scratch[2 * 128 + c], p3 = scratch[3 * 128 + c];
+    const float mx = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
+    float out = -INFINITY;
+    if (mx > -INFINITY)
+      out = mx + fast_log2(fast_exp2(p0 - mx) + fast_exp2(p1 - mx) + fast_exp2(p2 - mx) + fast_exp2(p3 - mx));
+    const int gj = n_base + c;
+    if (FULL || gj < N) ep.col_part[(size_t)m_blk * N + gj] = out;
+  }
+}
+
+// K2a: dS = g * ( 2^(a*sl2 - rl2') + 2^(a*sl2 - cl2'_j) ) - g*w_diag*[label], the (non-negative) weights folded
+// into the exponent offsets (one FFMA + one MUFU per term).  scratch[0..127] = per-column offsets cl2'.
+// Returns this thread's partial of sum dS_ij * a_ij (= d logit_scale).
+template <bool FULL>
+__device__ __forceinline__ float ds_tile(const EpiParams& ep, uint32_t taddr, const float* scratch, int gi, int n_base,
+                                         float nrl2, int lane, int M, int N) {
+  const float sl2 = ep.scale_p[0] * kLog2e;
+  const float g = ep.grad_out[0];
+  const float gwd = g * ep.w_diag;
+  const bool row_ok = FULL || gi < M;
+  const int lab = gi + ep.label_offset;
+  float dsp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + ch * 32, r);
+    tmem_ld_wait();
+    const int c0 = n_base + ch * 32;
+    float d[32];
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 c4 = *reinterpret_cast<const float4*>(scratch + ch * 32 + j4 * 4);
+      const float ncl2[4] = {-c4.x, -c4.y, -c4.z, -c4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j4 * 4 + u;
+        const float a = __uint_as_float(r[j]);
+        // out-of-range rows / columns carry offset -inf: their terms are exactly 0 (and are never stored)
+        d[j] = g * (fast_exp2(fmaf(a, sl2, nrl2)) + fast_exp2(fmaf(a, sl2, ncl2[u])));
+      }
+    }
+    if (row_ok && lab >= c0 && lab < c0 + 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d[j] = (lab - c0 == j) ? d[j] - gwd : d[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dsp[j & 3] = fmaf(d[j], __uint_as_float(r[j]), dsp[j & 3]);
+    if (row_ok) {
+      __nv_bfloat16* dst = ep.dS + (size_t)gi * ep.ldds + c0;
+      if (FULL || c0 + 32 <= N) {
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          uint4 pk;
+          __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) hp[u] = __floats2bfloat162_rn(d[j8 * 8 + 2 * u], d[j8 * 8 + 2 * u + 1]);
+          *reinterpret_cast<uint4*>(dst + j8 * 8) = pk;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < N) dst[j] = __float2bfloat16_rn(d[j]);
+      }
+      if (ep.dST != nullptr) {
+        // transposed copy (A/B-testing layout only): for a fixed column the warp writes 32 consecutive rows
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (FULL || c0 + j < N) ep.dST[(size_t)(c0 + j) * ep.lddst + gi] = __float2bfloat16_rn(d[j]);
+      }
+    }
+  }
+  return (dsp[0] + dsp[1]) + (dsp[2] + dsp[3]);
+}
+
+// plain GEMM epilogue: C = alpha * acc (fp32 or bf16)
+__device__ __forceinline__ void store_tile(const EpiParams& ep, uint32_t taddr, int gi, int n_base, int M, int N) {
+  const float alpha = ep.alpha * (ep.alpha_p ? ep.alpha_p[0] : 1.f);
+  const bool row_ok = gi < M;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + ch * 32, r);
+    tmem_ld_wait();
+    const int c0 = n_base + ch * 32;
+    if (!row_ok) continue;
+    if (ep.c_is_bf16) {
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.C) + (size_t)gi * ep.ldc + c0;
+      if (c0 + 32 <= N && (ep.ldc % 8) == 0) {
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          uint4 pk;
+          __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            hp[u] = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 2 * u]) * alpha,
+                                          __uint_as_float(r[j8 * 8 + 2 * u + 1]) * alpha);
+          *reinterpret_cast<uint4*>(dst + j8 * 8) = pk;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < N) dst[j] = __float2bfloat16_rn(__uint_as_float(r[j]) * alpha);
+      }
+    } else {
+      float* dst = reinterpret_cast<float*>(ep.C) + (size_t)gi * ep.ldc + c0;
+      if (c0 + 32 <= N && (ep.ldc % 4) == 0) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<float4*>(dst + j4 * 4) =
+              make_float4(__uint_as_float(r[j4 * 4]) * alpha, __uint_as_float(r[j4 * 4 + 1]) * alpha,
+                          __uint_as_float(r[j4 * 4 + 2]) * alpha, __uint_as_float(r[j4 * 4 + 3]) * alpha);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < N) dst[j] = __uint_as_float(r[j]) * alpha;
+      }
+    }
+  }
 }
 
 // A_MN / B_MN: the operand is stored "MN-major": global tensor [K rows][M or N contiguous] (e.g. dS read as the
@@ -103,8 +356,11 @@ template <int EPI, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                int M, int N, int K, EpiParams ep) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment is required by the 128B-swizzle atoms; align inside the shared window with pointer
+  // arithmetic on the __shared__ array itself so the compiler keeps emitting LDS/STS (a uintptr_t round trip turns
+  // every access into a generic LD/ST: measured as "lg" stalls in the epilogue)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* full_bar = bars;                      // [kStages]
@@ -229,234 +485,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tile_coords(tile, num_m, num_n, m_blk, n_blk);
       const int gi = m_blk * BM + q * 32 + lane;          // this thread's row
       const int n_base = n_blk * BN + h * 128;            // first column of this warp's half
-      const bool row_ok = gi < M;
+      // interior tiles (no ragged edge in this warp's 32 x 128 block) take the branch-free code
+      const bool interior = (m_blk * BM + q * 32 + 32 <= M) && (n_base + 128 <= N);
       float* scratch = epi_scratch + ((acc * 2 + h) * 4) * 128;   // [4][128] for this (acc, half)
-
-      if constexpr (EPI == EPI_DS) {
-        // stage log2-domain column LSEs of this half in smem before touching TMEM
-        const int c = q * 32 + lane;
-        const int gj = n_base + c;
-        scratch[c] = (gj < N) ? ep.col_lse[gj] * kLog2e : 0.f;
-        named_bar_sync(bar_id, 128);
-      }
-
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + h * 128);
+      const uint32_t tfull = smem_u32(&tfull_bar[acc]);
+      const uint32_t tempty = smem_u32(&tempty_bar[acc]);
 
       if constexpr (EPI == EPI_LSE) {
-        const float sl2 = ep.scale_p[0] * kLog2e;
-        float m_run = -INFINITY, l_run = 0.f;
-        const int lab = gi + ep.label_offset;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + ch * 32, r);
-          tmem_ld_wait();
-          const int c0 = n_base + ch * 32;
-          float v[32];
-          float cm = -INFINITY, vmin = INFINITY;
-          if (c0 + 32 <= N) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = __uint_as_float(r[j]) * sl2;
-              cm = fmaxf(cm, v[j]);
-              vmin = fminf(vmin, v[j]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const bool col_ok = (c0 + j) < N;
-              const float s = __uint_as_float(r[j]) * sl2;
-              v[j] = col_ok ? s : -INFINITY;
-              cm = fmaxf(cm, v[j]);
-              vmin = col_ok ? fminf(vmin, s) : vmin;
-            }
-          }
-          if (row_ok && lab >= c0 && lab < c0 + 32) {
-            float dv = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dv = (lab - c0 == j) ? v[j] : dv;
-            ep.diag[gi] = dv * kLn2;
-          }
-          // ---- one exponential per element, referenced to this row's chunk maximum ----
-          //   row   : sum_j 2^(v_ij - cm_i), folded into the running (max, sum) with two scalar exps
-          //   column: 2^(v_ij - W) = e_ij * 2^(cm_i - W) with W = max of cm over the warp's 32 rows, so the same
-          //           exponentials serve the column sums.  Exact unless an element lies more than 2^-kRange below
-          //           W (it would flush to zero while possibly dominating its own column): such chunks -- only
-          //           ever seen when a 32x32 block spans > 83 nats -- take the exact two-exp path below.
-          constexpr float kRange = 120.f;
-          float e[32];
-          float rsum = 0.f;
-          const float cm_safe = (cm > -INFINITY) ? cm : 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            e[j] = fast_exp2(v[j] - cm_safe);
-            rsum += e[j];
-          }
-          if (cm > -INFINITY) {
-            const float m_new = fmaxf(m_run, cm);
-            l_run = l_run * fast_exp2(m_run - m_new) + rsum * fast_exp2(cm - m_new);
-            m_run = m_new;
-          }
-          const float W = warp_max(row_ok ? cm : -INFINITY);
-          const float lo = -warp_max(row_ok ? -vmin : -INFINITY);
-          float* cslot = scratch + q * 128 + ch * 32;
-          if (W - lo <= kRange) {
-            // fast path (warp-uniform branch)
-            const float f = (row_ok && cm > -INFINITY) ? fast_exp2(cm - W) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) e[j] *= f;
-            warp_transpose_reduce<false>(e, lane);              // e[0] = sum over rows of column `lane`
-            cslot[lane] = (e[0] > 0.f) ? W + fast_log2(e[0]) : -INFINITY;
-          } else {
-            // exact path: per-column maximum, then a second exponential
-            float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = row_ok ? v[j] : -INFINITY;
-            warp_transpose_reduce<true>(x, lane);               // x[0] = max of column `lane`
-            cslot[lane] = x[0];
-            __syncwarp();
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 c4 = *reinterpret_cast<const float4*>(cslot + j4 * 4);
-              const float cmx[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int j = j4 * 4 + u;
-                // column with no valid entry: max = -inf -> contributes nothing
-                e[j] = (row_ok && cmx[u] > -INFINITY) ? fast_exp2(v[j] - cmx[u]) : 0.f;
-              }
-            }
-            __syncwarp();
-            const float my_cmax = x[0];
-            warp_transpose_reduce<false>(e, lane);
-            cslot[lane] = (e[0] > 0.f) ? my_cmax + fast_log2(e[0]) : -INFINITY;
-          }
-        }
-        // row partial for this (n tile, half)
-        if (row_ok)
-          ep.row_part[(size_t)(n_blk * 2 + h) * M + gi] = (l_run > 0.f) ? m_run + fast_log2(l_run) : -INFINITY;
-        // TMEM reads of this warp are complete: release the accumulator early
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-        // combine the four quadrant partials of each column
-        named_bar_sync(bar_id, 128);
+        mbar_wait(tfull, acc_phase);
+        tc_fence_after();
+        if (interior) lse_tile<true>(ep, taddr, scratch, gi, n_base, m_blk, n_blk, h, q, lane, M, N, tempty, bar_id);
+        else          lse_tile<false>(ep, taddr, scratch, gi, n_base, m_blk, n_blk, h, q, lane, M, N, tempty, bar_id);
+      } else if constexpr (EPI == EPI_DS) {
+        // stage the per-column exponent offsets of this half in smem before touching TMEM:
+        //   w_col * 2^(v - collse2) = 2^(v - (collse2 - log2 w_col)); w_col == 0 -> offset +inf -> term vanishes
         {
           const int c = q * 32 + lane;
-          const float p0 = scratch[0 * 128 + c], p1 = scratch[1 * 128 + c];
-          const float p2 = scratch[2 * 128 + c], p3 = scratch[3 * 128 + c];
-          const float mx = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
-          float out = -INFINITY;
-          if (mx > -INFINITY)
-            out = mx + fast_log2(fast_exp2(p0 - mx) + fast_exp2(p1 - mx) + fast_exp2(p2 - mx) + fast_exp2(p3 - mx));
           const int gj = n_base + c;
-          if (gj < N) ep.col_part[(size_t)m_blk * N + gj] = out;
+          const float lwc = (ep.w_col > 0.f) ? fast_log2(ep.w_col) : -INFINITY;
+          scratch[c] = (gj < N) ? ep.col_lse[gj] * kLog2e - lwc : INFINITY;
         }
-      } else if constexpr (EPI == EPI_DS) {
-        const float sl2 = ep.scale_p[0] * kLog2e;
-        const float g = ep.grad_out[0];
-        const float wr = ep.w_row * g, wc = ep.w_col * g, wd = ep.w_diag * g;
-        const float rl2 = row_ok ? ep.row_lse[gi] * kLog2e : 0.f;
-        const int lab = gi + ep.label_offset;
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + ch * 32, r);
-          tmem_ld_wait();
-          const int c0 = n_base + ch * 32;
-          float d[32];
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 c4 = *reinterpret_cast<const float4*>(scratch + ch * 32 + j4 * 4);
-            const float cl2[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int j = j4 * 4 + u;
-              const float a = __uint_as_float(r[j]);
-              const float v = a * sl2;
-              float dd = wr * fast_exp2(v - rl2) + wc * fast_exp2(v - cl2[u]);
-              dd = (lab == c0 + j) ? dd - wd : dd;
-              dd = (row_ok && (c0 + j) < N) ? dd : 0.f;
-              d[j] = dd;
-              dscale_acc = fmaf(dd, a, dscale_acc);
-            }
-          }
-          if (row_ok) {
-            __nv_bfloat16* dst = ep.dS + (size_t)gi * ep.ldds + c0;
-            if (c0 + 32 <= N) {
-#pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                uint4 pk;
-                __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) hp[u] = __floats2bfloat162_rn(d[j8 * 8 + 2 * u], d[j8 * 8 + 2 * u + 1]);
-                *reinterpret_cast<uint4*>(dst + j8 * 8) = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < N) dst[j] = __float2bfloat16_rn(d[j]);
-            }
-          }
-          if (ep.dST != nullptr && row_ok) {
-            // transposed copy: for a fixed column the warp writes 32 consecutive rows (64 B)
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < N) ep.dST[(size_t)(c0 + j) * ep.lddst + gi] = __float2bfloat16_rn(d[j]);
-          }
-        }
+        const float lwr = (ep.w_row > 0.f) ? fast_log2(ep.w_row) : -INFINITY;
+        const float nrl2 = (gi < M) ? -(ep.row_lse[gi] * kLog2e - lwr) : -INFINITY;      // -(rl2 - log2 w_row)
+        named_bar_sync(bar_id, 128);
+        mbar_wait(tfull, acc_phase);
+        tc_fence_after();
+        if (interior) dscale_acc += ds_tile<true>(ep, taddr, scratch, gi, n_base, nrl2, lane, M, N);
+        else          dscale_acc += ds_tile<false>(ep, taddr, scratch, gi, n_base, nrl2, lane, M, N);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (lane == 0) mbar_arrive(tempty);
       } else {
-        // ---------------- EPI_STORE ----------------
-        const float alpha = ep.alpha * (ep.alpha_p ? ep.alpha_p[0] : 1.f);
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + ch * 32, r);
-          tmem_ld_wait();
-          const int c0 = n_base + ch * 32;
-          if (row_ok) {
-            if (ep.c_is_bf16) {
-              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(ep.C) + (size_t)gi * ep.ldc + c0;
-              if (c0 + 32 <= N && (ep.ldc % 8) == 0) {
-#pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {
-                  uint4 pk;
-                  __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-                  for (int u = 0; u < 4; ++u)
-                    hp[u] = __floats2bfloat162_rn(__uint_as_float(r[j8 * 8 + 2 * u]) * alpha,
-                                                  __uint_as_float(r[j8 * 8 + 2 * u + 1]) * alpha);
-                  *reinterpret_cast<uint4*>(dst + j8 * 8) = pk;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (c0 + j < N) dst[j] = __float2bfloat16_rn(__uint_as_float(r[j]) * alpha);
-              }
-            } else {
-              float* dst = reinterpret_cast<float*>(ep.C) + (size_t)gi * ep.ldc + c0;
-              if (c0 + 32 <= N && (ep.ldc % 4) == 0) {
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4)
-                  *reinterpret_cast<float4*>(dst + j4 * 4) =
-                      make_float4(__uint_as_float(r[j4 * 4]) * alpha, __uint_as_float(r[j4 * 4 + 1]) * alpha,
-                                  __uint_as_float(r[j4 * 4 + 2]) * alpha, __uint_as_float(r[j4 * 4 + 3]) * alpha);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (c0 + j < N) dst[j] = __uint_as_float(r[j]) * alpha;
-              }
-            }
-          }
-        }
+        mbar_wait(tfull, acc_phase);
+        tc_fence_after();
+        store_tile(ep, taddr, gi, n_base, M, N);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (lane == 0) mbar_arrive(tempty);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;

@@ -10,9 +10,21 @@ template <typename T>
 int xattn_simt_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                    void* dq, void* dk, void* dv, int b, int Lq, int Lk, int heads, int dh, int ldq, int ldk, int ldv,
                    float sm_scale, float p_drop, uint64_t seed, uint64_t offset, cudaStream_t st);
+bool xattn_mma_supported(int Lq, int dh);
+int xattn_mma_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int b, int Lq, int Lk, int heads,
+                  int dh, int ldq, int ldk, int ldv, float sm_scale, float p_drop, uint64_t seed, uint64_t offset,
+                  cudaStream_t st);
 }  // namespace xtag
 
 using namespace xtag;
+
+// the tensor-core / TMA kernel needs bf16 operands that TMA can describe
+static bool mma_eligible(const void* q, const void* k, const void* v, int dtype, int Lq, int dh, int heads, int ldq,
+                         int ldk, int ldv) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return dtype == XTAG_BF16 && xattn_mma_supported(Lq, dh) && al(q) && al(k) && al(v) && ldq % 8 == 0 &&
+         ldk % 8 == 0 && ldv % 8 == 0 && (heads * dh) % 8 == 0;
+}
 
 static int check_common(const char* who, int dtype, int b, int Lq, int Lk, int heads, int dh, int ldq, int ldk, int ldv,
                         float p) {
@@ -31,6 +43,8 @@ extern "C" int xtag_xattn_fwd(const void* q, const void* k, const void* v, int d
   int rc = check_common("xattn_fwd", dtype, b, Lq, Lk, heads, dh, ldq, ldk, ldv, dropout_p);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (mma_eligible(q, k, v, dtype, Lq, dh, heads, ldq, ldk, ldv))
+    return xattn_mma_fwd(q, k, v, o, lse, b, Lq, Lk, heads, dh, ldq, ldk, ldv, softmax_scale, dropout_p, seed, offset, st);
   if (dtype == XTAG_F32)
     return xattn_simt_fwd<float>(q, k, v, o, lse, b, Lq, Lk, heads, dh, ldq, ldk, ldv, softmax_scale, dropout_p, seed, offset, st);
   return xattn_simt_fwd<__nv_bfloat16>(q, k, v, o, lse, b, Lq, Lk, heads, dh, ldq, ldk, ldv, softmax_scale, dropout_p, seed,

@@ -1,0 +1,314 @@
+// K4, bf16 production path: flash-style cross-attention core of the XTag tag head.
+// Reference: BertSelfAttention.forward cross branch (src/open_clip/tagging_heads/bert.py:219-274):
+//   P = softmax(q k^T / sqrt(dh)) ; P = dropout(P) ; ctx = P v      per (sample, head); Lq = 44 tag queries,
+//   Lk = 50 / 197 / 257 ViT tokens, 4 heads x 192.
+//
+// HBM-bound ((88 + 2 N) * 1536 bytes per sample-layer, ~36 flop/byte), so the design goal is to
+// stream K and V exactly once at full bandwidth:
+//   * one CTA per (sample, head), 16 query rows per warp (3 warps for Lq = 44), several CTAs resident per SM
+//   * Q, K, V tiles arrive by TMA (cp.async.bulk.tensor.3d, 128B swizzle, zero-filled past Lq / Lk) into a
+//     2-stage smem ring signalled through mbarriers; the next K/V tile is in flight while the current one is used
+//   * QK^T and PV on tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate; operands via ldmatrix on the swizzled
+//     tiles); online softmax in the log2 domain with warp-shuffle row reductions; P never leaves registers
+//   * Philox keep-mask for the attention-probability dropout (training), regenerated in the backward
+// tcgen05 is deliberately not used here: M = 44 rows per problem cannot fill a 128-row UMMA tile and the kernel is
+// bandwidth-bound, not tensor-bound.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "philox.cuh"
+#include "tc_ptx.cuh"
+
+namespace xtag {
+
+using namespace ptx;
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// byte offset of element (row, col) inside a [rows][64 bf16] tile written by TMA with CU_TENSOR_MAP_SWIZZLE_128B
+// (col must be a multiple of 8: one 16-byte unit)
+__device__ __forceinline__ uint32_t swz(int row, int col) {
+  return (uint32_t)(row * 128 + ((((col >> 3) ^ row) & 7) << 4));
+}
+
+constexpr int XA_KT = 32;        // keys per pipeline stage
+constexpr int XA_MAXW = 4;       // up to 64 query rows
+
+// NCH = dh / 64
+template <int NCH>
+__global__ void __launch_bounds__(32 * XA_MAXW)
+xattn_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
+                     int Lq, int Lk, int heads, float sl2, float p_drop, uint64_t seed, uint64_t offset) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nw = blockDim.x >> 5;
+  const int QROWS = 16 * nw;
+  const uint32_t q_bytes = (uint32_t)NCH * QROWS * 128;
+  constexpr uint32_t kv_chunk = XA_KT * 128;                  // one 64-column chunk of a K or V tile
+  constexpr uint32_t stage_bytes = 2 * NCH * kv_chunk;        // K then V
+  uint8_t* Qs = smem;
+  uint8_t* KVs = smem + ((q_bytes + 1023) & ~1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(KVs + 2 * stage_bytes);   // [0] = Q, [1..2] = stages
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  const int dh = NCH * 64;
+  const int num_tiles = (Lk + XA_KT - 1) / XA_KT;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue_tile = [&](int t) {
+    const int st = t & 1;
+    const uint32_t fb = smem_u32(&bars[1 + st]);
+    const uint32_t base = smem_u32(KVs + st * stage_bytes);
+    mbar_arrive_expect_tx(fb, stage_bytes);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      tma_load_3d(base + c * kv_chunk, &tmK, fb, h * dh + c * 64, t * XA_KT, b);
+      tma_load_3d(base + (NCH + c) * kv_chunk, &tmV, fb, h * dh + c * 64, t * XA_KT, b);
+    }
+  };
+  if (tid == 0) {
+    const uint32_t qb = smem_u32(&bars[0]);
+    mbar_arrive_expect_tx(qb, q_bytes);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) tma_load_3d(smem_u32(Qs) + c * QROWS * 128, &tmQ, qb, h * dh + c * 64, 0, b);
+    issue_tile(0);
+  }
+
+  const int g = lane >> 2, t4 = lane & 3;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float oacc[NCH * 8][4];
+#pragma unroll
+  for (int i = 0; i < NCH * 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
+
+  mbar_wait(smem_u32(&bars[0]), 0);
+  const uint32_t q_base = smem_u32(Qs);
+  const int qrow = warp * 16 + (lane & 15);                 // ldmatrix row supplied by this lane (A operand)
+  const int row0 = warp * 16 + g;                           // accumulator rows owned: row0 and row0 + 8
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+
+  for (int t = 0; t < num_tiles; ++t) {
+    const int st = t & 1;
+    if (tid == 0 && t + 1 < num_tiles) issue_tile(t + 1);   // stage st^1 was released by the barrier below
+    mbar_wait(smem_u32(&bars[1 + st]), (uint32_t)((t >> 1) & 1));
+    const uint32_t k_base = smem_u32(KVs + st * stage_bytes);
+    const uint32_t v_base = k_base + NCH * kv_chunk;
+
+    // ---- S = Q K^T for this warp's 16 rows x XA_KT keys ----
+    float sacc[XA_KT / 8][4];
+#pragma unroll
+    for (int i = 0; i < XA_KT / 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sacc[i][j] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NCH * 4; ++kk) {
+      const int c = kk >> 2, kx = (kk & 3) * 16;
+      uint32_t a[4];
+      ldsm_x4(q_base + c * QROWS * 128 + swz(qrow, kx + ((lane >> 4) << 3)), a);
+#pragma unroll
+      for (int np = 0; np < XA_KT / 16; ++np) {
+        // four 8x8 blocks: (keys 0-7, k 0-7), (keys 0-7, k 8-15), (keys 8-15, k 0-7), (keys 8-15, k 8-15)
+        const int krow = np * 16 + ((lane >> 4) << 3) + (lane & 7);
+        const int kcol = kx + (((lane >> 3) & 1) << 3);
+        uint32_t bb[4];
+        ldsm_x4(k_base + c * kv_chunk + swz(krow, kcol), bb);
+        mma_bf16(sacc[2 * np], a, bb[0], bb[1]);
+        mma_bf16(sacc[2 * np + 1], a, bb[2], bb[3]);
+      }
+    }
+    // ---- scale (log2 domain), mask keys past Lk, online softmax ----
+    const int key0 = t * XA_KT;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < XA_KT / 8; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = key0 + i * 8 + t4 * 2 + (j & 1);
+        const float s = (key < Lk) ? sacc[i][j] * sl2 : -INFINITY;
+        sacc[i][j] = s;
+        mx[j >> 1] = fmaxf(mx[j >> 1], s);
+      }
+    }
+    float corr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);            // every tile holds >= 1 valid key, so m_new is finite
+      corr[r] = fast_exp2(m_run[r] - m_new);
+      m_run[r] = m_new;
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < XA_KT / 8; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float p = fast_exp2(sacc[i][j] - m_run[j >> 1]);
+        rs[j >> 1] += p;
+        sacc[i][j] = p;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];      // quad-partial sums, reduced at the end
+    if (p_drop > 0.f) {
+      // dropout acts on the normalised probabilities; the normaliser is linear, so masking the unnormalised
+      // numerators (after the row sum above) is equivalent
+#pragma unroll
+      for (int i = 0; i < XA_KT / 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int key = key0 + i * 8 + t4 * 2 + (j & 1);
+          const int row = row0 + ((j >> 1) << 3);
+          const uint64_t idx = ((uint64_t)bh * Lq + row) * Lk + key;
+          sacc[i][j] = philox_keep(seed, offset, idx, p_drop) ? sacc[i][j] * keep_scale : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NCH * 8; ++i) {
+      oacc[i][0] *= corr[0]; oacc[i][1] *= corr[0];
+      oacc[i][2] *= corr[1]; oacc[i][3] *= corr[1];
+    }
+    // ---- O += P V ----
+#pragma unroll
+    for (int ks = 0; ks < XA_KT / 16; ++ks) {
+      uint32_t a[4];
+      a[0] = pack_bf16(sacc[2 * ks][0], sacc[2 * ks][1]);
+      a[1] = pack_bf16(sacc[2 * ks][2], sacc[2 * ks][3]);
+      a[2] = pack_bf16(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
+      a[3] = pack_bf16(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
+#pragma unroll
+      for (int dn = 0; dn < NCH * 4; ++dn) {
+        // transposed 8x8 blocks: (keys 0-7, d 0-7), (keys 8-15, d 0-7), (keys 0-7, d 8-15), (keys 8-15, d 8-15)
+        const int vrow = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+        const int vcol = dn * 16 + ((lane >> 4) << 3);
+        uint32_t bb[4];
+        ldsm_x4_t(v_base + (vcol >> 6) * kv_chunk + swz(vrow, vcol & 63), bb);
+        mma_bf16(oacc[2 * dn], a, bb[0], bb[1]);
+        mma_bf16(oacc[2 * dn + 1], a, bb[2], bb[3]);
+      }
+    }
+    __syncthreads();                                         // stage st may be refilled from here on
+  }
+
+  // ---- finalize: normalise, store ctx (bf16) and the row log-sum-exp (natural log) ----
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const int HD = heads * dh;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = row0 + r * 8;
+    if (row >= Lq) continue;
+    const float inv = 1.f / l_run[r];
+    __nv_bfloat16* orow = o + ((size_t)b * Lq + row) * HD + h * dh;
+#pragma unroll
+    for (int i = 0; i < NCH * 8; ++i)
+      *reinterpret_cast<uint32_t*>(orow + i * 8 + t4 * 2) = pack_bf16(oacc[i][2 * r] * inv, oacc[i][2 * r + 1] * inv);
+    if (t4 == 0) lse[(size_t)bh * Lq + row] = (m_run[r] + fast_log2(l_run[r])) * kLn2;
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled xa_get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// [b][L][cols] bf16 tensor, row stride ld elements, batch stride L*ld; box = [1][box_rows][64]
+static int xa_make_tmap(CUtensorMap* tm, const void* base, int b, int L, int cols, long ld, int box_rows) {
+  PFN_encodeTiled enc = xa_get_encode();
+  XTAG_REQUIRE(enc != nullptr, XTAG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  XTAG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0, XTAG_ERR_UNSUPPORTED,
+               "xattn(mma): operands must be 16-byte aligned with 16-byte multiple row strides");
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)b};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * (cuuint64_t)ld * 2};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XTAG_REQUIRE(r == CUDA_SUCCESS, XTAG_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+  return XTAG_OK;
+}
+
+bool xattn_mma_supported(int Lq, int dh) { return (dh == 64 || dh == 128 || dh == 192 || dh == 256) && Lq <= 16 * XA_MAXW; }
+
+template <int NCH>
+static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, void* o, float* lse, int b,
+                      int Lq, int Lk, int heads, float sl2, float p, uint64_t seed, uint64_t offset, cudaStream_t st) {
+  const int nw = (Lq + 15) / 16;
+  const size_t q_bytes = ((size_t)NCH * 16 * nw * 128 + 1023) & ~(size_t)1023;
+  const size_t smem = 1024 + q_bytes + 2 * (2 * NCH * XA_KT * 128) + 64;
+  XTAG_CUDA(cudaFuncSetAttribute(xattn_fwd_mma_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  xattn_fwd_mma_kernel<NCH><<<b * heads, 32 * nw, smem, st>>>(tq, tk, tv, (__nv_bfloat16*)o, lse, Lq, Lk, heads, sl2, p,
+                                                              seed, offset);
+  XTAG_CHECK_LAUNCH();
+  return XTAG_OK;
+}
+
+int xattn_mma_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int b, int Lq, int Lk, int heads,
+                  int dh, int ldq, int ldk, int ldv, float sm_scale, float p_drop, uint64_t seed, uint64_t offset,
+                  cudaStream_t st) {
+  CUtensorMap tq, tk, tv;
+  const int nw = (Lq + 15) / 16;
+  int rc = xa_make_tmap(&tq, q, b, Lq, heads * dh, ldq, 16 * nw);
+  if (rc) return rc;
+  rc = xa_make_tmap(&tk, k, b, Lk, heads * dh, ldk, XA_KT);
+  if (rc) return rc;
+  rc = xa_make_tmap(&tv, v, b, Lk, heads * dh, ldv, XA_KT);
+  if (rc) return rc;
+  const float sl2 = sm_scale * kLog2e;
+  switch (dh / 64) {
+    case 1: return launch_fwd<1>(tq, tk, tv, o, lse, b, Lq, Lk, heads, sl2, p_drop, seed, offset, st);
+    case 2: return launch_fwd<2>(tq, tk, tv, o, lse, b, Lq, Lk, heads, sl2, p_drop, seed, offset, st);
+    case 3: return launch_fwd<3>(tq, tk, tv, o, lse, b, Lq, Lk, heads, sl2, p_drop, seed, offset, st);
+    default: return launch_fwd<4>(tq, tk, tv, o, lse, b, Lq, Lk, heads, sl2, p_drop, seed, offset, st);
+  }
+}
+
+}  // namespace xtag
