@@ -19,6 +19,7 @@
 //   warps 4-11  epilogue      : tcgen05.ld 32x32b (lane = row), 2 warps per TMEM lane quadrant, each owning
 //                               one 128-column half of the accumulator
 #include <cuda.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -37,7 +38,9 @@ constexpr int kThreads = 128 + 32 * kEpiWarps;   // 384
 constexpr int kTmemCols = 512;
 constexpr int kGroupM = 16;
 constexpr int kEpiScratchFloats = 2 /*acc*/ * 2 /*half*/ * 4 /*quadrant*/ * 128;   // 8 KB
-constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 256 /*barriers*/ + kEpiScratchFloats * 4;
+constexpr int kOutStageBytes = kEpiWarps * 2048;   // per epilogue warp: one 32-row x 64-byte tile for the dS TMA store
+constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 256 /*barriers*/ + kEpiScratchFloats * 4 +
+                           kOutStageBytes;
 
 enum { EPI_LSE = 0, EPI_DS = 1, EPI_STORE = 2 };
 
@@ -105,6 +108,11 @@ __device__ __forceinline__ float select32(const uint32_t (&r)[32], int idx) {
 #pragma unroll
   for (int k = 0; k < 2; ++k) t2[k] = (idx & 2) ? t4[k + 2] : t4[k];
   return (idx & 1) ? t2[1] : t2[0];
+}
+
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -243,7 +251,8 @@ __device__ __forceinline__ void lse_tile(const EpiParams& ep, uint32_t taddr, fl
 // into the exponent offsets (one FFMA + one MUFU per term).  scratch[0..127] = per-column offsets cl2'.
 // Returns this thread's partial of sum dS_ij * a_ij (= d logit_scale).
 template <bool FULL>
-__device__ __forceinline__ float ds_tile(const EpiParams& ep, uint32_t taddr, const float* scratch, int gi, int n_base,
+__device__ __forceinline__ float ds_tile(const EpiParams& ep, const CUtensorMap* tmC, uint32_t taddr,
+                                         const float* scratch, uint32_t ostage, int gi, int row_blk, int n_base,
                                          float nrl2, int lane, int M, int N) {
   const float sl2 = ep.scale_p[0] * kLog2e;
   const float g = ep.grad_out[0];
@@ -276,28 +285,36 @@ __device__ __forceinline__ float ds_tile(const EpiParams& ep, uint32_t taddr, co
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) dsp[j & 3] = fmaf(d[j], __uint_as_float(r[j]), dsp[j & 3]);
-    if (row_ok) {
+    // ---- store: 32 rows x 64 B of bf16 through shared memory and one TMA tile store per warp and chunk.
+    // Direct STG would write 16 B per 128-B line per instruction (32 L2 requests per warp instruction, measured as
+    // the kernel's dominant stall); the TMA store issues full 64-B row segments and clips ragged edges itself.
+    if (ep.dST == nullptr) {
+      if (lane == 0) tma_store_wait_read();                 // previous tile store has drained this buffer
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t p0 = pack2_bf16(d[u * 8 + 0], d[u * 8 + 1]), p1 = pack2_bf16(d[u * 8 + 2], d[u * 8 + 3]);
+        uint32_t p2 = pack2_bf16(d[u * 8 + 4], d[u * 8 + 5]), p3 = pack2_bf16(d[u * 8 + 6], d[u * 8 + 7]);
+        // CU_TENSOR_MAP_SWIZZLE_64B: 16-byte unit index (bits 4-5) ^= address bits 7-8 (= (row >> 1) & 3)
+        const uint32_t off = (uint32_t)(lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ostage + off), "r"(p0), "r"(p1), "r"(p2), "r"(p3)
+                     : "memory");
+      }
+      fence_proxy_async();                                  // generic-proxy writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, ostage, c0, row_blk);
+        tma_store_commit();
+      }
+    } else if (row_ok) {
+      // A/B-testing layout (XTAG_TC_BWD_LAYOUT=transposed): direct stores of dS and dS^T
       __nv_bfloat16* dst = ep.dS + (size_t)gi * ep.ldds + c0;
-      if (FULL || c0 + 32 <= N) {
 #pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          uint4 pk;
-          __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) hp[u] = __floats2bfloat162_rn(d[j8 * 8 + 2 * u], d[j8 * 8 + 2 * u + 1]);
-          *reinterpret_cast<uint4*>(dst + j8 * 8) = pk;
+      for (int j = 0; j < 32; ++j)
+        if (FULL || c0 + j < N) {
+          dst[j] = __float2bfloat16_rn(d[j]);
+          ep.dST[(size_t)(c0 + j) * ep.lddst + gi] = __float2bfloat16_rn(d[j]);
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < N) dst[j] = __float2bfloat16_rn(d[j]);
-      }
-      if (ep.dST != nullptr) {
-        // transposed copy (A/B-testing layout only): for a fixed column the warp writes 32 consecutive rows
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (FULL || c0 + j < N) ep.dST[(size_t)(c0 + j) * ep.lddst + gi] = __float2bfloat16_rn(d[j]);
-      }
     }
   }
   return (dsp[0] + dsp[1]) + (dsp[2] + dsp[3]);
@@ -355,20 +372,23 @@ __device__ __forceinline__ void store_tile(const EpiParams& ep, uint32_t taddr, 
 template <int EPI, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               int M, int N, int K, EpiParams ep) {
+               const __grid_constant__ CUtensorMap tmC, int M, int N, int K, EpiParams ep) {
   // 1024-byte alignment is required by the 128B-swizzle atoms; align inside the shared window with pointer
   // arithmetic on the __shared__ array itself so the compiler keeps emitting LDS/STS (a uintptr_t round trip turns
   // every access into a generic LD/ST: measured as "lg" stalls in the epilogue)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  // layout: [operand ring | dS store staging (both 1024-byte aligned: swizzle patterns use absolute address bits)
+  //          | mbarriers + TMEM pointer (256 B) | epilogue scratch]
+  uint8_t* out_stage = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kOutStageBytes);
   uint64_t* full_bar = bars;                      // [kStages]
   uint64_t* empty_bar = bars + kStages;           // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;       // [2]
   uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  float* epi_scratch = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
+  float* epi_scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -511,8 +531,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         named_bar_sync(bar_id, 128);
         mbar_wait(tfull, acc_phase);
         tc_fence_after();
-        if (interior) dscale_acc += ds_tile<true>(ep, taddr, scratch, gi, n_base, nrl2, lane, M, N);
-        else          dscale_acc += ds_tile<false>(ep, taddr, scratch, gi, n_base, nrl2, lane, M, N);
+        const uint32_t ostage = smem_u32(out_stage + e * 2048);
+        const int row_blk = m_blk * BM + q * 32;
+        if (interior) dscale_acc += ds_tile<true>(ep, &tmC, taddr, scratch, ostage, gi, row_blk, n_base, nrl2, lane, M, N);
+        else          dscale_acc += ds_tile<false>(ep, &tmC, taddr, scratch, ostage, gi, row_blk, n_base, nrl2, lane, M, N);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty);
@@ -528,6 +550,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (acc == 0) acc_phase ^= 1;
     }
     if constexpr (EPI == EPI_DS) {
+      if (lane == 0) tma_store_wait_all();               // dS tiles fully written before the kernel ends
       dscale_acc = warp_sum(dscale_acc);
       if (lane == 0) ep.dscale_part[blockIdx.x * kEpiWarps + e] = dscale_acc;
     }
@@ -577,10 +600,29 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* base, int outer, int inne
 
 // acc[M,N] = sum_k A(m,k) B(n,k).  K-major operand: memory [M|N rows][K], row stride ld.
 //                                   MN-major operand: memory [K rows][M|N], row stride ld.
+// bf16 row-major [rows][cols] output written by 32 x 32 TMA tile stores (64-byte swizzle), clipped at the edges
+static int make_store_tmap_bf16(CUtensorMap* tm, void* base, int rows, int cols, long ld) {
+  PFN_encodeTiled enc = get_encode();
+  XTAG_REQUIRE(enc != nullptr, XTAG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XTAG_REQUIRE(r == CUDA_SUCCESS, XTAG_ERR_CUDA, "cuTensorMapEncodeTiled(store) failed with CUresult %d", (int)r);
+  return XTAG_OK;
+}
+
 template <int EPI, bool A_MN, bool B_MN>
 static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiParams& ep,
                      cudaStream_t st) {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  if (EPI == EPI_DS) {
+    int rcC = make_store_tmap_bf16(&tmC, ep.dS, M, N, ep.ldds);
+    if (rcC) return rcC;
+  }
   int rc = A_MN ? make_tmap_bf16(&tmA, A, K, M, lda, BK) : make_tmap_bf16(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
   rc = B_MN ? make_tmap_bf16(&tmB, B, K, N, ldb, BK) : make_tmap_bf16(&tmB, B, N, K, ldb, BN);
@@ -596,7 +638,7 @@ static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, in
   if (grid > num_tiles) grid = num_tiles;
   {
     ProfScope prof(EPI, 2.0 * (double)M * (double)N * (double)K, st);
-    tc_gemm_kernel<EPI, A_MN, B_MN><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, M, N, K, ep);
+    tc_gemm_kernel<EPI, A_MN, B_MN><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmC, M, N, K, ep);
   }
   XTAG_CHECK_LAUNCH();
   return XTAG_OK;
