@@ -78,7 +78,8 @@ int xtag_l2norm_bwd(const void* gy, int gy_dtype, const void* y, int y_dtype, co
  *         col_lse[j] = LSE_{i<M} S_ij        (PARTIAL over this rank's rows; combine across
  *                                             ranks with xtag_lse_combine)
  *         diag[i]    = S_{i, i+label_offset} (the label logit; label_offset = b*rank,
- *                                             loss.py:95-96)
+ *                                             loss.py:95-96).  label_offset = -1: this column block holds no
+ *                                             labels (chunk-pipelined gather), diag is left untouched.
  * ------------------------------------------------------------------------------------------- */
 size_t xtag_clip_fwd_ws_bytes(int M, int N, int D, int dtype, int impl);
 int xtag_clip_fwd(const void* A, const void* Bm, int dtype, int M, int N, int D,
@@ -112,7 +113,11 @@ int xtag_clip_bwd(const void* A, const void* Bm, int dtype, int M, int N, int D,
                   const float* row_lse, const float* col_lse,
                   float w_row, float w_col, float w_diag, const float* grad_out,
                   void* dA, void* dB, int grad_dtype, float* dscale,
-                  void* ws, size_t ws_bytes, int impl, void* stream);
+                  void* ws, size_t ws_bytes, int impl, int flags, void* stream);
+/* flags for xtag_clip_bwd */
+#define XTAG_BWD_REUSE_DS 1       /* ws already holds dS from a preceding call with the same operands and weights:
+                                     skip the dS producer and d(logit_scale) (lets a caller launch the dB GEMM, start
+                                     its reduce-scatter, and overlap it with the dA GEMM) */
 
 /* plain tcgen05 GEMM used by K2 and exported for bring-up tests:
  *   C[M,N] = alpha * A[M,K] * B[N,K]^T   (A, B bf16 row-major "K-major"; C f32 or bf16; alpha by value) */

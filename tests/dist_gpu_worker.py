@@ -32,17 +32,21 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     failures = []
+    # sizes keep the fp64 world emulation (W ranks x 4 modes on the host) to a few seconds even at W = 8
     for (b, D, scale, dtype, ltol, gtol) in [(48, 64, 14.285714, torch.float32, 1e-5, 1e-5),
                                              (256, 256, 30.0, torch.bfloat16, 1e-3, 2e-2),
-                                             (1024, 512, 14.285714, torch.bfloat16, 1e-3, 2e-2)]:
+                                             (384, 512, 14.285714, torch.bfloat16, 1e-3, 2e-2)]:
         g = torch.Generator().manual_seed(100 + b)
         I_all = torch.nn.functional.normalize(torch.randn(b * world, D, generator=g), dim=-1)
         T_all = torch.nn.functional.normalize(0.3 * I_all + 0.7 * torch.randn(b * world, D, generator=g), dim=-1)
         I_all, T_all = I_all.to(dtype), T_all.to(dtype)
         Il = [I_all[r * b:(r + 1) * b].double() for r in range(world)]
         Tl = [T_all[r * b:(r + 1) * b].double() for r in range(world)]
+        torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))
         for ll in (False, True):
             for gwg in (False, True):
+                if b == 384 and not (ll and gwg):
+                    continue                      # largest shape: performance mode only
                 losses, dI, dT, ds = oracle.clip_loss_world(Il, Tl, scale, ll, gwg)
                 I = I_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
                 T = T_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)

@@ -41,12 +41,18 @@ class ModelKernels:
         return gx.to(gx_dtype)
 
     # K1
-    def clip_fwd(self, A, Bm, scale, label_offset):
+    def clip_fwd(self, A, Bm, scale, label_offset, col_out=None, diag_out=None):
         self.calls.append(("clip_fwd", tuple(A.shape), tuple(Bm.shape), int(label_offset)))
         S = float(scale.reshape(-1)[0]) * (_f64(A) @ _f64(Bm).T)
         M = A.shape[0]
-        idx = torch.arange(M) + label_offset
-        return (torch.logsumexp(S, 1).float(), torch.logsumexp(S, 0).float(), S[torch.arange(M), idx].float())
+        col = torch.logsumexp(S, 0).float()
+        if col_out is not None:
+            col_out.copy_(col)
+            col = col_out
+        diag = diag_out if diag_out is not None else torch.zeros(M, dtype=torch.float32)
+        if label_offset >= 0:                      # -1: no labels in this column block, diag untouched
+            diag.copy_(S[torch.arange(M), torch.arange(M) + label_offset].float())
+        return torch.logsumexp(S, 1).float(), col, diag
 
     def lse_combine(self, parts):
         return torch.logsumexp(_f64(parts), 0).float()
@@ -58,7 +64,7 @@ class ModelKernels:
 
     # K2
     def clip_bwd(self, A, Bm, scale, label_offset, row_lse, col_lse, w_row, w_col, w_diag, grad_out,
-                 need_dA, need_dB, grad_dtype):
+                 need_dA, need_dB, grad_dtype, ws=None, reuse_ds=False, return_ws=False):
         self.calls.append(("clip_bwd", tuple(A.shape), tuple(Bm.shape), int(label_offset), w_row, w_col, w_diag))
         s = float(scale.reshape(-1)[0])
         g = float(grad_out.reshape(-1)[0])
@@ -74,7 +80,10 @@ class ModelKernels:
         dS = g * (dS - w_diag * eye)
         dA = (s * dS @ B64).to(grad_dtype) if need_dA else None
         dB = (s * dS.T @ A64).to(grad_dtype) if need_dB else None
-        return dA, dB, (dS * raw).sum().float()
+        ds = torch.zeros((), dtype=torch.float32) if reuse_ds else (dS * raw).sum().float()
+        if return_ws:
+            return dA, dB, ds, "ws"
+        return dA, dB, ds
 
     # K4
     @staticmethod

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libxtag_b200.so")
 
 XTAG_F32, XTAG_BF16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+BWD_REUSE_DS = 1
 
 _lib = None
 
@@ -33,7 +34,7 @@ SIGNATURES = {
     "xtag_clip_bwd_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "xtag_clip_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                               c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
-                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "xtag_tc_gemm_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "xtag_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "xtag_xattn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,

@@ -9,7 +9,7 @@ int simt_clip_fwd(const void* A, const void* Bm, int dtype, int M, int N, int D,
 int simt_clip_bwd(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale, int label_offset,
                   const float* row_lse, const float* col_lse, float w_row, float w_col, float w_diag,
                   const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
-                  void* ws, size_t ws_bytes, cudaStream_t st);
+                  void* ws, size_t ws_bytes, int flags, cudaStream_t st);
 size_t tc_fwd_ws(int M, int N);
 size_t tc_bwd_ws(int M, int N, int D);
 int tc_clip_fwd(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
@@ -17,7 +17,7 @@ int tc_clip_fwd(const void* A, const void* Bm, int M, int N, int D, const float*
 int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
                 const float* row_lse, const float* col_lse, float w_row, float w_col, float w_diag,
                 const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
-                void* ws, size_t ws_bytes, cudaStream_t st);
+                void* ws, size_t ws_bytes, int flags, cudaStream_t st);
 
 // tcgen05 path needs bf16 operands whose rows are 16-byte multiples (TMA global stride rule)
 static bool tc_eligible(int dtype, int D) { return dtype == XTAG_BF16 && D % 8 == 0; }
@@ -58,7 +58,7 @@ extern "C" int xtag_clip_fwd(const void* A, const void* Bm, int dtype, int M, in
   XTAG_REQUIRE(A && Bm && scale && row_lse && col_lse && diag, XTAG_ERR_INVALID, "clip_fwd: null pointer");
   XTAG_REQUIRE(M > 0 && N > 0 && D > 0, XTAG_ERR_INVALID, "clip_fwd: empty problem M=%d N=%d D=%d", M, N, D);
   XTAG_REQUIRE(dtype == XTAG_F32 || dtype == XTAG_BF16, XTAG_ERR_INVALID, "clip_fwd: bad dtype %d", dtype);
-  XTAG_REQUIRE(label_offset >= 0 && (long)label_offset + M <= (long)N, XTAG_ERR_INVALID,
+  XTAG_REQUIRE(label_offset == -1 || (label_offset >= 0 && (long)label_offset + M <= (long)N), XTAG_ERR_INVALID,
                "clip_fwd: labels [%d, %d) fall outside the %d columns", label_offset, label_offset + M, N);
   int rc = xtag_device_check();
   if (rc) return rc;
@@ -73,7 +73,7 @@ extern "C" int xtag_clip_fwd(const void* A, const void* Bm, int dtype, int M, in
 extern "C" int xtag_clip_bwd(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale,
                              int label_offset, const float* row_lse, const float* col_lse, float w_row, float w_col,
                              float w_diag, const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
-                             void* ws, size_t ws_bytes, int impl, void* stream) {
+                             void* ws, size_t ws_bytes, int impl, int flags, void* stream) {
   XTAG_REQUIRE(A && Bm && scale && row_lse && col_lse && grad_out, XTAG_ERR_INVALID, "clip_bwd: null pointer");
   XTAG_REQUIRE(M > 0 && N > 0 && D > 0, XTAG_ERR_INVALID, "clip_bwd: empty problem M=%d N=%d D=%d", M, N, D);
   XTAG_REQUIRE((dtype == XTAG_F32 || dtype == XTAG_BF16) && (grad_dtype == XTAG_F32 || grad_dtype == XTAG_BF16),
@@ -84,7 +84,7 @@ extern "C" int xtag_clip_bwd(const void* A, const void* Bm, int dtype, int M, in
   if (r < 0) return r;
   if (r == XTAG_IMPL_TC)
     return tc_clip_bwd(A, Bm, M, N, D, scale, label_offset, row_lse, col_lse, w_row, w_col, w_diag, grad_out, dA, dB,
-                       grad_dtype, dscale, ws, ws_bytes, (cudaStream_t)stream);
+                       grad_dtype, dscale, ws, ws_bytes, flags, (cudaStream_t)stream);
   return simt_clip_bwd(A, Bm, dtype, M, N, D, scale, label_offset, row_lse, col_lse, w_row, w_col, w_diag, grad_out,
-                       dA, dB, grad_dtype, dscale, ws, ws_bytes, (cudaStream_t)stream);
+                       dA, dB, grad_dtype, dscale, ws, ws_bytes, flags, (cudaStream_t)stream);
 }

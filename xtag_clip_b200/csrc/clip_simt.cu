@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) simt_clip_fwd_kernel(const T* __restrict_
       float l = 0.f;
       for (int c = 0; c < cols; ++c) l += exp2f(Ts[r][c] - mx);
       row_part[(size_t)blockIdx.x * M + m0 + r] = mx + log2f(l);
-      const int lab = m0 + r + label_offset;
+      const int lab = (label_offset < 0) ? -1 : m0 + r + label_offset;
       if (lab >= n0 && lab < n0 + cols) diag[m0 + r] = Ts[r][lab - n0] * kLn2;
     }
   } else if (tid < 2 * TS) {
@@ -98,20 +98,41 @@ __global__ void __launch_bounds__(256) simt_clip_fwd_kernel(const T* __restrict_
 }
 
 // out[i] = out_mul * log2( sum_p 2^(parts[p*n + i] * in_mul) )        (in_mul/out_mul convert ln <-> log2)
+// 256 threads = 32 consecutive i (coalesced 128-byte rows of `parts`) x 8 interleaved groups of p; each thread keeps
+// an online (max, sum) over its parts, the 8 groups are merged through shared memory.
 __global__ void __launch_bounds__(256) lse_reduce_kernel(const float* __restrict__ parts, int P, int n,
                                                          float in_mul, float out_mul, float* __restrict__ out) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    float mx = -INFINITY;
-    for (int p = 0; p < P; ++p) mx = fmaxf(mx, parts[(size_t)p * n + i] * in_mul);
-    float l = 0.f;
-    for (int p = 0; p < P; ++p) l += exp2f(parts[(size_t)p * n + i] * in_mul - mx);
-    out[i] = (mx + log2f(l)) * out_mul;
+  __shared__ float sm_m[8][33], sm_l[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i0 = blockIdx.x * 32; i0 < n; i0 += gridDim.x * 32) {
+    const int i = i0 + tx;
+    float m = -INFINITY, l = 0.f;
+    if (i < n) {
+      for (int p = ty; p < P; p += 8) {
+        const float v = parts[(size_t)p * n + i] * in_mul;
+        if (v > m) { l = l * exp2f(m - v) + 1.f; m = v; }      // exp2f(-inf) == 0 covers the first element
+        else if (v > -INFINITY) l += exp2f(v - m);
+      }
+    }
+    sm_m[ty][tx] = m;
+    sm_l[ty][tx] = l;
+    __syncthreads();
+    if (ty == 0 && i < n) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) mx = fmaxf(mx, sm_m[g][tx]);
+      float tot = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) tot += (sm_m[g][tx] > -INFINITY) ? sm_l[g][tx] * exp2f(sm_m[g][tx] - mx) : 0.f;
+      out[i] = (mx + log2f(tot)) * out_mul;
+    }
+    __syncthreads();
   }
 }
 
 int launch_lse_reduce(const float* parts, int P, int n, float in_mul, float out_mul, float* out, cudaStream_t st) {
-  int blocks = (n + 255) / 256;
-  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  int blocks = (n + 31) / 32;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
   if (blocks < 1) blocks = 1;
   lse_reduce_kernel<<<blocks, 256, 0, st>>>(parts, P, n, in_mul, out_mul, out);
   XTAG_CHECK_LAUNCH();
@@ -258,18 +279,21 @@ int simt_clip_fwd(const void* A, const void* Bm, int dtype, int M, int N, int D,
 template <typename T, typename TG>
 static int simt_bwd(const T* A, const T* Bm, int M, int N, int D, const float* scale, int label_offset,
                     const float* row_lse, const float* col_lse, float w_row, float w_col, float w_diag,
-                    const float* grad_out, TG* dA, TG* dB, float* dscale, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    const float* grad_out, TG* dA, TG* dB, float* dscale, void* ws, size_t ws_bytes, int flags,
+                    cudaStream_t st) {
   const int ntm = (M + TS - 1) / TS, ntn = (N + TS - 1) / TS;
   const size_t need = ((size_t)M * N + (size_t)ntm * ntn) * sizeof(float);
   XTAG_REQUIRE(ws && ws_bytes >= need, XTAG_ERR_WORKSPACE, "clip_bwd(simt): workspace %zu < %zu", ws_bytes, need);
   float* dS = (float*)ws;
   float* part = dS + (size_t)M * N;
-  simt_clip_ds_kernel<T><<<dim3(ntn, ntm), 256, 0, st>>>(A, Bm, M, N, D, scale, label_offset, row_lse, col_lse,
-                                                          w_row, w_col, w_diag, grad_out, dS, part);
-  XTAG_CHECK_LAUNCH();
-  if (dscale) {
-    int rc = launch_sum_into(part, ntm * ntn, dscale, st);
-    if (rc) return rc;
+  if (!(flags & XTAG_BWD_REUSE_DS)) {
+    simt_clip_ds_kernel<T><<<dim3(ntn, ntm), 256, 0, st>>>(A, Bm, M, N, D, scale, label_offset, row_lse, col_lse,
+                                                            w_row, w_col, w_diag, grad_out, dS, part);
+    XTAG_CHECK_LAUNCH();
+    if (dscale) {
+      int rc = launch_sum_into(part, ntm * ntn, dscale, st);
+      if (rc) return rc;
+    }
   }
   const int ntd = (D + TS - 1) / TS;
   if (dA) {   // dA[i,d] = scale * sum_j dS[i,j] Bm[j,d]
@@ -286,19 +310,19 @@ static int simt_bwd(const T* A, const T* Bm, int M, int N, int D, const float* s
 int simt_clip_bwd(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale, int label_offset,
                   const float* row_lse, const float* col_lse, float w_row, float w_col, float w_diag,
                   const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
-                  void* ws, size_t ws_bytes, cudaStream_t st) {
+                  void* ws, size_t ws_bytes, int flags, cudaStream_t st) {
   typedef __nv_bfloat16 bf16;
   if (dtype == XTAG_F32 && grad_dtype == XTAG_F32)
     return simt_bwd<float, float>((const float*)A, (const float*)Bm, M, N, D, scale, label_offset, row_lse, col_lse,
-                                  w_row, w_col, w_diag, grad_out, (float*)dA, (float*)dB, dscale, ws, ws_bytes, st);
+                                  w_row, w_col, w_diag, grad_out, (float*)dA, (float*)dB, dscale, ws, ws_bytes, flags, st);
   if (dtype == XTAG_BF16 && grad_dtype == XTAG_F32)
     return simt_bwd<bf16, float>((const bf16*)A, (const bf16*)Bm, M, N, D, scale, label_offset, row_lse, col_lse,
-                                 w_row, w_col, w_diag, grad_out, (float*)dA, (float*)dB, dscale, ws, ws_bytes, st);
+                                 w_row, w_col, w_diag, grad_out, (float*)dA, (float*)dB, dscale, ws, ws_bytes, flags, st);
   if (dtype == XTAG_BF16 && grad_dtype == XTAG_BF16)
     return simt_bwd<bf16, bf16>((const bf16*)A, (const bf16*)Bm, M, N, D, scale, label_offset, row_lse, col_lse,
-                                w_row, w_col, w_diag, grad_out, (bf16*)dA, (bf16*)dB, dscale, ws, ws_bytes, st);
+                                w_row, w_col, w_diag, grad_out, (bf16*)dA, (bf16*)dB, dscale, ws, ws_bytes, flags, st);
   return simt_bwd<float, bf16>((const float*)A, (const float*)Bm, M, N, D, scale, label_offset, row_lse, col_lse,
-                               w_row, w_col, w_diag, grad_out, (bf16*)dA, (bf16*)dB, dscale, ws, ws_bytes, st);
+                               w_row, w_col, w_diag, grad_out, (bf16*)dA, (bf16*)dB, dscale, ws, ws_bytes, flags, st);
 }
 
 }  // namespace xtag

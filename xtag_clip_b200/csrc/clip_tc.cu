@@ -139,7 +139,7 @@ __device__ __forceinline__ void lse_tile(const EpiParams& ep, uint32_t taddr, fl
   constexpr float kRange = 120.f;
   const float sl2 = ep.scale_p[0] * kLog2e;
   const bool row_ok = FULL || gi < M;
-  const int lab = gi + ep.label_offset;
+  const int lab = (ep.label_offset < 0) ? -1 : gi + ep.label_offset;      // -1: no labels in this column block
   float m_run = -INFINITY, l_run = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < 4; ++ch) {
@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(256) transpose_pad_bf16_kernel(const __nv_bflo
 int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
                 const float* row_lse, const float* col_lse, float w_row, float w_col, float w_diag,
                 const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
-                void* ws, size_t ws_bytes, cudaStream_t st) {
+                void* ws, size_t ws_bytes, int flags, cudaStream_t st) {
   const BwdLayout L = bwd_layout(M, N, D);
   const bool tr = bwd_transposed_layout();
   XTAG_REQUIRE(ws && ws_bytes >= L.total, XTAG_ERR_WORKSPACE, "clip_bwd(tc): workspace %zu < %zu", ws_bytes, L.total);
@@ -743,26 +743,29 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
   __nv_bfloat16* Bt = (__nv_bfloat16*)(w + L.off_bt);
   float* part = (float*)(w + L.off_part);
 
-  // padding columns of dS (N not a multiple of 8) enter the K sum of dA: keep them zero
-  if (L.Np != (size_t)N) XTAG_CUDA(cudaMemsetAsync(dS, 0, (size_t)M * L.Np * 2, st));
-  if (tr && dB && L.Mp != (size_t)M) XTAG_CUDA(cudaMemsetAsync(dST, 0, (size_t)N * L.Mp * 2, st));
+  int rc = XTAG_OK;
+  if (!(flags & XTAG_BWD_REUSE_DS)) {
+    // padding columns of dS (N not a multiple of 8) enter the K sum of dA: keep them zero
+    if (L.Np != (size_t)N) XTAG_CUDA(cudaMemsetAsync(dS, 0, (size_t)M * L.Np * 2, st));
+    if (tr && dB && L.Mp != (size_t)M) XTAG_CUDA(cudaMemsetAsync(dST, 0, (size_t)N * L.Mp * 2, st));
 
-  EpiParams ep = {};
-  ep.scale_p = scale;
-  ep.label_offset = label_offset;
-  ep.row_lse = row_lse;
-  ep.col_lse = col_lse;
-  ep.w_row = w_row; ep.w_col = w_col; ep.w_diag = w_diag;
-  ep.grad_out = grad_out;
-  ep.dS = dS; ep.ldds = (int)L.Np;
-  ep.dST = (tr && dB) ? dST : nullptr; ep.lddst = (int)L.Mp;
-  ep.dscale_part = part;
-  const int grid = tc_grid_for(M, N);
-  int rc = launch_tc<EPI_DS, false, false>(A, D, Bm, D, M, N, D, ep, st);
-  if (rc) return rc;
-  if (dscale) {
-    rc = launch_sum_into(part, grid * kEpiWarps, dscale, st);
+    EpiParams ep = {};
+    ep.scale_p = scale;
+    ep.label_offset = label_offset;
+    ep.row_lse = row_lse;
+    ep.col_lse = col_lse;
+    ep.w_row = w_row; ep.w_col = w_col; ep.w_diag = w_diag;
+    ep.grad_out = grad_out;
+    ep.dS = dS; ep.ldds = (int)L.Np;
+    ep.dST = (tr && dB) ? dST : nullptr; ep.lddst = (int)L.Mp;
+    ep.dscale_part = part;
+    const int grid = tc_grid_for(M, N);
+    rc = launch_tc<EPI_DS, false, false>(A, D, Bm, D, M, N, D, ep, st);
     if (rc) return rc;
+    if (dscale) {
+      rc = launch_sum_into(part, grid * kEpiWarps, dscale, st);
+      if (rc) return rc;
+    }
   }
   EpiParams es = {};
   es.ldc = D; es.c_is_bf16 = (grad_dtype == XTAG_BF16); es.alpha = 1.f; es.alpha_p = scale;

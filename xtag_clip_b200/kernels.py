@@ -73,9 +73,11 @@ class CudaKernels:
         return gx.reshape(y.shape)
 
     # ---- K1 ----------------------------------------------------------------------------------
-    def clip_fwd(self, A: torch.Tensor, Bm: torch.Tensor, scale: torch.Tensor, label_offset: int
+    def clip_fwd(self, A: torch.Tensor, Bm: torch.Tensor, scale: torch.Tensor, label_offset: int,
+                 col_out: Optional[torch.Tensor] = None, diag_out: Optional[torch.Tensor] = None
                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """-> (row_lse [M], col_lse_partial [N], diag [M]), fp32, natural-log units."""
+        """-> (row_lse [M], col_lse_partial [N], diag [M]), fp32, natural-log units.  label_offset = -1: the column
+        block holds no labels (diag untouched).  col_out / diag_out: write into these (contiguous) buffers."""
         _cuda(A, Bm, scale)
         assert A.dtype == Bm.dtype and A.dim() == 2 and Bm.dim() == 2 and A.shape[1] == Bm.shape[1]
         A, Bm = A.contiguous(), Bm.contiguous()
@@ -83,8 +85,9 @@ class CudaKernels:
         N = Bm.shape[0]
         dev = A.device
         row_lse = torch.empty(M, dtype=torch.float32, device=dev)
-        col_lse = torch.empty(N, dtype=torch.float32, device=dev)
-        diag = torch.empty(M, dtype=torch.float32, device=dev)
+        col_lse = col_out if col_out is not None else torch.empty(N, dtype=torch.float32, device=dev)
+        diag = diag_out if diag_out is not None else torch.empty(M, dtype=torch.float32, device=dev)
+        assert col_lse.is_contiguous() and col_lse.numel() == N and diag.is_contiguous() and diag.numel() == M
         nbytes = int(self.lib.xtag_clip_fwd_ws_bytes(M, N, D, _dt(A), self.impl))
         if nbytes == 0:
             check(-1, "xtag_clip_fwd_ws_bytes")
@@ -111,8 +114,10 @@ class CudaKernels:
 
     # ---- K2 ----------------------------------------------------------------------------------
     def clip_bwd(self, A, Bm, scale, label_offset, row_lse, col_lse, w_row, w_col, w_diag, grad_out,
-                 need_dA: bool, need_dB: bool, grad_dtype: torch.dtype):
-        """-> (dA [M,D] | None, dB [N,D] | None, dscale 0-d fp32)"""
+                 need_dA: bool, need_dB: bool, grad_dtype: torch.dtype, ws: Optional[torch.Tensor] = None,
+                 reuse_ds: bool = False, return_ws: bool = False):
+        """-> (dA [M,D] | None, dB [N,D] | None, dscale 0-d fp32[, ws]).  reuse_ds: `ws` is the workspace of a
+        preceding call with the same operands/weights, its staged dS is reused (dscale is then 0)."""
         _cuda(A, Bm, scale, row_lse, col_lse, grad_out)
         A, Bm = A.contiguous(), Bm.contiguous()
         M, D = A.shape
@@ -125,11 +130,16 @@ class CudaKernels:
         nbytes = int(self.lib.xtag_clip_bwd_ws_bytes(M, N, D, _dt(A), self.impl))
         if nbytes == 0:
             check(-1, "xtag_clip_bwd_ws_bytes")
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if ws is None:
+            assert not reuse_ds
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        assert ws.numel() >= nbytes
         check(self.lib.xtag_clip_bwd(_p(A), _p(Bm), _dt(A), M, N, D, _p(scale), int(label_offset),
                                      _p(row_lse), _p(col_lse), float(w_row), float(w_col), float(w_diag), _p(g),
-                                     _p(dA), _p(dB), _DT[grad_dtype], _p(dscale), _p(ws), nbytes, self.impl,
-                                     _stream()), "xtag_clip_bwd")
+                                     _p(dA), _p(dB), _DT[grad_dtype], _p(dscale), _p(ws), ws.numel(), self.impl,
+                                     _lib.BWD_REUSE_DS if reuse_ds else 0, _stream()), "xtag_clip_bwd")
+        if return_ws:
+            return dA, dB, dscale, ws
         return dA, dB, dscale
 
     def tc_gemm_nt(self, A: torch.Tensor, B: torch.Tensor, out_dtype=torch.float32, alpha: float = 1.0):

@@ -50,6 +50,56 @@ except ImportError:  # pragma: no cover
 class _Comm:
     def __init__(self, world_size: int, rank: int, group=None):
         self.world_size, self.rank, self.group = world_size, rank, group
+        self._side = None
+
+    # -- stream helpers (no-ops for CPU tensors, so the same schedule runs under gloo in the CPU tests) --------
+    def side_stream(self, device):
+        if device.type != "cuda":
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
+
+    def chunk_groups(self):
+        """Ranks are exchanged in groups of G consecutive ranks (G = 2 from 4 ranks on: 2b columns per kernel
+        launch keep the 148 SMs in whole waves); returns (G, number of groups, own group)."""
+        W = self.world_size
+        G = 2 if (W >= 4 and W % 2 == 0) else 1
+        return G, W // G, self.rank // G
+
+    def pipelined_gather(self, x: torch.Tensor, out_all: torch.Tensor):
+        """Chunk-pipelined all-gather of [b, D] blocks into out_all [W*b, D] (rank order).  Round 0 exchanges
+        inside the rank's own group, round j sends to group g+j and receives group g-j (batched NCCL P2P on a side
+        stream).  Returns [(row_lo, row_hi, event | None)] in arrival order: the caller consumes block k while
+        block k+1 is still in flight.  Replaces the blocking torch.distributed.nn.all_gather of loss.py:51-52."""
+        W, r = self.world_size, self.rank
+        b = x.shape[0]
+        G, NG, g0 = self.chunk_groups()
+        side = self.side_stream(x.device)
+        out_all[r * b:(r + 1) * b].copy_(x)
+        plan = []
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+        ctx = torch.cuda.stream(side) if side is not None else _NullCtx()
+        with ctx:
+            for j in range(NG):
+                send_grp, recv_grp = (g0 + j) % NG, (g0 - j) % NG
+                ops = []
+                for m in range(G):
+                    ps, pr = send_grp * G + m, recv_grp * G + m
+                    if ps != r:
+                        ops.append(dist.P2POp(dist.isend, x, ps, group=self.group))
+                    if pr != r:
+                        ops.append(dist.P2POp(dist.irecv, out_all[pr * b:(pr + 1) * b], pr, group=self.group))
+                if ops:
+                    for req in dist.batch_isend_irecv(ops):
+                        req.wait()
+                ev = None
+                if side is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                plan.append((recv_grp * G * b, (recv_grp + 1) * G * b, ev))
+        return plan
 
     def all_gather_cat(self, x: torch.Tensor) -> torch.Tensor:
         """[b, ...] on every rank -> [W*b, ...] in rank order (what torch.cat(all_gather) gives)."""
@@ -73,6 +123,14 @@ class _Comm:
         return out
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 @dataclass
 class _Cfg:
     local_loss: bool
@@ -82,6 +140,7 @@ class _Cfg:
     kernels: object
     comm: Optional[_Comm]
     comm_dtype: Optional[torch.dtype]
+    pipeline: bool = True
 
 
 def _as_scale_tensor(logit_scale, device) -> torch.Tensor:
@@ -102,6 +161,27 @@ class _FusedClipLoss(torch.autograd.Function):
         if W == 1:
             off = 0
             row_lse, col_lse, diag = K.clip_fwd(img, txt, scale, 0)
+        elif cfg.local_loss and cfg.gather_with_grad and cfg.pipeline:
+            # performance mode: chunk-pipelined gather, K1 runs on column block k while block k+1 is in flight
+            off = b * r
+            B = b * W
+            txt_all = torch.empty((B, txt.shape[1]), dtype=txt.dtype, device=txt.device)
+            plan = cfg.comm.pipelined_gather(txt, txt_all)
+            col_part = torch.empty(B, dtype=torch.float32, device=txt.device)
+            diag = torch.empty(b, dtype=torch.float32, device=txt.device)
+            row_parts = []
+            for lo, hi, ev in plan:
+                if ev is not None:
+                    torch.cuda.current_stream().wait_event(ev)
+                lab = off - lo if lo <= off < hi else -1          # only the rank's own block holds its labels
+                rp, _, _ = K.clip_fwd(img, txt_all[lo:hi], scale, lab, col_out=col_part[lo:hi], diag_out=diag)
+                row_parts.append(rp)
+            row_lse = K.lse_combine(torch.stack(row_parts)) if len(row_parts) > 1 else row_parts[0]
+            side = cfg.comm.side_stream(txt.device)
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)     # sends of `txt` done before it can be freed
+            parts = cfg.comm.all_gather_cat(col_part.reshape(1, -1))      # [W, B]
+            col_lse = K.lse_combine(parts)
         elif cfg.local_loss:
             off = b * r
             txt_all = cfg.comm.all_gather_cat(txt)
@@ -136,12 +216,31 @@ class _FusedClipLoss(torch.autograd.Function):
                                           need_i, need_t, fdt)
         elif cfg.local_loss and cfg.gather_with_grad:
             cdt = cfg.comm_dtype or fdt
-            d_img, d_txt_all, ds = K.clip_bwd(img, txt_all, scale, off, row_lse, col_lse, 0.5 / b, 0.5 / b, 1.0 / b,
-                                              g, need_i, need_t, cdt if need_t else fdt)
-            if need_i and d_img.dtype != fdt:
-                d_img = d_img.to(fdt)
-            if need_t:
-                d_txt = cfg.comm.reduce_scatter_sum(d_txt_all).to(fdt)
+            w = (0.5 / b, 0.5 / b, 1.0 / b)
+            side = cfg.comm.side_stream(img.device) if cfg.pipeline else None
+            if need_t and need_i and cfg.pipeline:
+                # dS + dB GEMM first, reduce-scatter of the [B, D] partial on the side stream while the dA GEMM
+                # (which reuses the staged dS) runs on the main stream
+                _, d_txt_all, ds, ws = K.clip_bwd(img, txt_all, scale, off, row_lse, col_lse, *w, g, False, True, cdt,
+                                                  return_ws=True)
+                if side is not None:
+                    side.wait_stream(torch.cuda.current_stream())
+                    d_txt_all.record_stream(side)
+                with (torch.cuda.stream(side) if side is not None else _NullCtx()):
+                    d_txt = cfg.comm.reduce_scatter_sum(d_txt_all)
+                d_img, _, _ = K.clip_bwd(img, txt_all, scale, off, row_lse, col_lse, *w, g, True, False, fdt,
+                                         ws=ws, reuse_ds=True)
+                if side is not None:
+                    torch.cuda.current_stream().wait_stream(side)
+                    d_txt.record_stream(torch.cuda.current_stream())
+                d_txt = d_txt.to(fdt)
+            else:
+                d_img, d_txt_all, ds = K.clip_bwd(img, txt_all, scale, off, row_lse, col_lse, *w, g, need_i, need_t,
+                                                  cdt if need_t else fdt)
+                if need_i and d_img.dtype != fdt:
+                    d_img = d_img.to(fdt)
+                if need_t:
+                    d_txt = cfg.comm.reduce_scatter_sum(d_txt_all).to(fdt)
         elif cfg.local_loss:
             ds = torch.zeros((), dtype=torch.float32, device=img.device)
             if need_i or need_s:
@@ -226,6 +325,7 @@ class ClipLoss(nn.Module):
             *,
             group=None,
             comm_dtype: Optional[torch.dtype] = None,
+            pipeline: bool = True,
             _kernels=None,
     ):
         super().__init__()
@@ -240,7 +340,9 @@ class ClipLoss(nn.Module):
         self.use_horovod = use_horovod
         self._group = group
         self._comm_dtype = comm_dtype
+        self._pipeline = pipeline
         self._kernels = _kernels
+        self._comm = None
 
         # cache state
         self.prev_num_logits = 0
@@ -286,8 +388,11 @@ class ClipLoss(nn.Module):
         comm = None
         if self.world_size > 1:
             assert has_distributed, 'torch.distributed did not import correctly, please use a PyTorch version with support.'
-            comm = _Comm(self.world_size, self.rank, self._group)
-        return _Cfg(self.local_loss, self.gather_with_grad, self.rank, self.world_size, k, comm, self._comm_dtype)
+            if self._comm is None:
+                self._comm = _Comm(self.world_size, self.rank, self._group)     # keeps its side stream
+            comm = self._comm
+        return _Cfg(self.local_loss, self.gather_with_grad, self.rank, self.world_size, k, comm, self._comm_dtype,
+                    self._pipeline)
 
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
         if image_features.dim() != 2 or image_features.shape != text_features.shape:
