@@ -115,7 +115,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -127,11 +127,28 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                       "-i", str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-i", str(self.idx), "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def wait_first_sample(self, timeout=20.0):
+        """nvidia-smi takes a second or more to initialise (and holds driver locks while it does): the timed
+        region must not start before the sampler is in steady state."""
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.05)
+
+    @staticmethod
+    def _ts(s):
+        import datetime
+        try:
+            return datetime.datetime.strptime(s.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
+
+    def stop(self, t_lo=None, t_hi=None):
         if self.p is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.p.terminate()
@@ -146,6 +163,9 @@ class ClockSampler:
         for r in rows:
             try:
                 r = [x.strip() for x in r]
+                ts = self._ts(r[0])
+                if t_lo is not None and ts is not None and not (t_lo - 0.25 <= ts <= t_hi + 0.25):
+                    continue                      # keep only samples taken during the timed region
                 sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
                 names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
                 for n, v in zip(names, r[5:9]):
@@ -154,7 +174,7 @@ class ClockSampler:
             except Exception:
                 continue
         if not sm:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples inside the timed region"])
         loaded = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
         return dict(sm_mhz=statistics.median(loaded), sm_max_mhz=max(mx), reasons=sorted(reasons),
                     samples=len(sm), power_w_max=max(power))
@@ -202,26 +222,39 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        sampler.wait_first_sample()
     for _ in range(W):
         loss = step(I_dev, T_dev)
     barrier()
 
     # ---- device-resident leg (value) ----
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
     n0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_lo = time.time()
     e0.record()
     for _ in range(K):
         loss = step(I_dev, T_dev)
     e1.record()
     barrier()
+    t_hi = time.time()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
-    clocks = sampler.stop() if sampler else None
+    # a timed region shorter than the 200 ms sampling period yields no clock sample: keep the SAME steps running
+    # (untimed, on every rank -- the steps contain collectives) until a few samples under this exact load exist
+    ms_max = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_max, op=dist.ReduceOp.MAX)
+    if float(ms_max) < 600.0:
+        extra = int(800.0 / max(float(ms_max) / K, 1e-3)) + 1
+        for _ in range(extra):
+            step(I_dev, T_dev)
+        barrier()
+        t_hi = time.time()
+    clocks = sampler.stop(t_lo, t_hi) if sampler else None
     loss_val = float(loss.item())
 
     # ---- end-to-end leg: host buffers in, loss out, copies inside the timed region ----

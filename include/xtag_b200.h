@@ -91,6 +91,14 @@ int xtag_clip_fwd(const void* A, const void* Bm, int dtype, int M, int N, int D,
  * all-gather (the one exchange step of the sharded loss). */
 int xtag_lse_combine(const float* parts, int W, int N, float* out, void* stream);
 
+/* Peer-memory variants for the NVLink exchange steps (pointers in `*_dev` are DEVICE arrays of W device pointers,
+ * one per rank, into peer-mapped symmetric buffers):
+ *   xtag_lse_combine_ptrs : out[j] = log sum_w exp(parts[w][j])            (column-LSE exchange, forward)
+ *   xtag_sum_ptrs_bf16    : out[i] = sum_w parts[w][i], n bf16 elements    (reduce step of the pull-based
+ *                                                                           reduce-scatter of the text gradient) */
+int xtag_lse_combine_ptrs(const float* const* parts_dev, int W, int N, float* out, void* stream);
+int xtag_sum_ptrs_bf16(const void* const* parts_dev, int W, size_t n, void* out, void* stream);
+
 /* loss = 0.5 * [ mean_i(row_lse_i - diag_i) + mean_i(col_lse[label_offset+i] - diag_i) ]
  * (loss.py:134-137 with the two cross-entropies written out).  loss_out[0] is overwritten. */
 int xtag_clip_loss(const float* row_lse, const float* diag, const float* col_lse,

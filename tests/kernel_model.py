@@ -64,7 +64,7 @@ class ModelKernels:
 
     # K2
     def clip_bwd(self, A, Bm, scale, label_offset, row_lse, col_lse, w_row, w_col, w_diag, grad_out,
-                 need_dA, need_dB, grad_dtype, ws=None, reuse_ds=False, return_ws=False):
+                 need_dA, need_dB, grad_dtype, ws=None, reuse_ds=False, return_ws=False, dB_out=None):
         self.calls.append(("clip_bwd", tuple(A.shape), tuple(Bm.shape), int(label_offset), w_row, w_col, w_diag))
         s = float(scale.reshape(-1)[0])
         g = float(grad_out.reshape(-1)[0])

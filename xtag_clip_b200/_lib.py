@@ -30,6 +30,8 @@ SIGNATURES = {
     "xtag_clip_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "xtag_lse_combine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "xtag_lse_combine_ptrs": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "xtag_sum_ptrs_bf16": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),
     "xtag_clip_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "xtag_clip_bwd_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "xtag_clip_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,

@@ -325,9 +325,71 @@ int simt_clip_bwd(const void* A, const void* Bm, int dtype, int M, int N, int D,
                                w_row, w_col, w_diag, grad_out, (bf16*)dA, (bf16*)dB, dscale, ws, ws_bytes, flags, st);
 }
 
+// ---- peer-memory reductions (NVLink loads from symmetric buffers of the other ranks) -------------------------------
+// out[j] = ln sum_w exp(parts[w][j]); parts[w] is rank w's buffer (peer-mapped device pointer)
+__global__ void __launch_bounds__(256) lse_combine_ptrs_kernel(const float* const* __restrict__ parts, int W, int n,
+                                                               float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float v[16];
+    float mx = -INFINITY;
+    for (int w = 0; w < W; ++w) {
+      v[w] = parts[w][i] * kLog2e;
+      mx = fmaxf(mx, v[w]);
+    }
+    float l = 0.f;
+    for (int w = 0; w < W; ++w) l += exp2f(v[w] - mx);
+    out[i] = (mx + log2f(l)) * kLn2;
+  }
+}
+
+// out[i] = sum_w parts[w][i]  (bf16 in, fp32 accumulate, bf16 out): the reduce step of the pull-based reduce-scatter
+__global__ void __launch_bounds__(256) sum_ptrs_bf16_kernel(const __nv_bfloat16* const* __restrict__ parts, int W,
+                                                            size_t n8, __nv_bfloat16* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < W; ++w) {
+      const uint4 r = *reinterpret_cast<const uint4*>(parts[w] + i * 8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(h[k]);
+        acc[2 * k] += f.x;
+        acc[2 * k + 1] += f.y;
+      }
+    }
+    uint4 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ho[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+    *reinterpret_cast<uint4*>(out + i * 8) = o;
+  }
+}
+
 }  // namespace xtag
 
 using namespace xtag;
+
+extern "C" int xtag_lse_combine_ptrs(const float* const* parts_dev, int W, int N, float* out, void* stream) {
+  XTAG_REQUIRE(parts_dev && out && W > 0 && W <= 16 && N >= 0, XTAG_ERR_INVALID, "lse_combine_ptrs: bad arguments");
+  if (N == 0) return XTAG_OK;
+  int blocks = (N + 255) / 256;
+  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  lse_combine_ptrs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(parts_dev, W, N, out);
+  XTAG_CHECK_LAUNCH();
+  return XTAG_OK;
+}
+
+extern "C" int xtag_sum_ptrs_bf16(const void* const* parts_dev, int W, size_t n, void* out, void* stream) {
+  XTAG_REQUIRE(parts_dev && out && W > 0 && n % 8 == 0, XTAG_ERR_INVALID, "sum_ptrs_bf16: bad arguments (n %% 8 == 0)");
+  if (n == 0) return XTAG_OK;
+  const size_t n8 = n / 8;
+  size_t blocks = (n8 + 255) / 256;
+  if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
+  sum_ptrs_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16* const*)parts_dev, W, n8,
+                                                                     (__nv_bfloat16*)out);
+  XTAG_CHECK_LAUNCH();
+  return XTAG_OK;
+}
 
 extern "C" int xtag_lse_combine(const float* parts, int W, int N, float* out, void* stream) {
   XTAG_REQUIRE(parts && out && W > 0 && N >= 0, XTAG_ERR_INVALID, "lse_combine: bad arguments");

@@ -105,6 +105,19 @@ class CudaKernels:
         check(self.lib.xtag_lse_combine(_p(parts), W, N, _p(out), _stream()), "xtag_lse_combine")
         return out
 
+    def lse_combine_ptrs(self, ptrs_dev: torch.Tensor, W: int, N: int) -> torch.Tensor:
+        """ptrs_dev: int64 CUDA tensor of W peer-mapped fp32 buffer addresses."""
+        _cuda(ptrs_dev)
+        out = torch.empty(N, dtype=torch.float32, device=ptrs_dev.device)
+        check(self.lib.xtag_lse_combine_ptrs(_p(ptrs_dev), W, N, _p(out), _stream()), "xtag_lse_combine_ptrs")
+        return out
+
+    def sum_ptrs_bf16(self, ptrs_dev: torch.Tensor, W: int, shape) -> torch.Tensor:
+        _cuda(ptrs_dev)
+        out = torch.empty(shape, dtype=torch.bfloat16, device=ptrs_dev.device)
+        check(self.lib.xtag_sum_ptrs_bf16(_p(ptrs_dev), W, out.numel(), _p(out), _stream()), "xtag_sum_ptrs_bf16")
+        return out
+
     def clip_loss(self, row_lse: torch.Tensor, diag: torch.Tensor, col_lse: torch.Tensor, label_offset: int):
         _cuda(row_lse, diag, col_lse)
         out = torch.empty((), dtype=torch.float32, device=row_lse.device)
@@ -115,7 +128,7 @@ class CudaKernels:
     # ---- K2 ----------------------------------------------------------------------------------
     def clip_bwd(self, A, Bm, scale, label_offset, row_lse, col_lse, w_row, w_col, w_diag, grad_out,
                  need_dA: bool, need_dB: bool, grad_dtype: torch.dtype, ws: Optional[torch.Tensor] = None,
-                 reuse_ds: bool = False, return_ws: bool = False):
+                 reuse_ds: bool = False, return_ws: bool = False, dB_out: Optional[torch.Tensor] = None):
         """-> (dA [M,D] | None, dB [N,D] | None, dscale 0-d fp32[, ws]).  reuse_ds: `ws` is the workspace of a
         preceding call with the same operands/weights, its staged dS is reused (dscale is then 0)."""
         _cuda(A, Bm, scale, row_lse, col_lse, grad_out)
@@ -124,7 +137,10 @@ class CudaKernels:
         N = Bm.shape[0]
         dev = A.device
         dA = torch.empty((M, D), dtype=grad_dtype, device=dev) if need_dA else None
-        dB = torch.empty((N, D), dtype=grad_dtype, device=dev) if need_dB else None
+        dB = None
+        if need_dB:
+            dB = dB_out if dB_out is not None else torch.empty((N, D), dtype=grad_dtype, device=dev)
+            assert dB.is_contiguous() and dB.shape == (N, D) and dB.dtype == grad_dtype
         dscale = torch.zeros((), dtype=torch.float32, device=dev)
         g = grad_out.detach().to(torch.float32).reshape(1).contiguous()
         nbytes = int(self.lib.xtag_clip_bwd_ws_bytes(M, N, D, _dt(A), self.impl))

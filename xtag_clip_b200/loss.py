@@ -51,6 +51,24 @@ class _Comm:
     def __init__(self, world_size: int, rank: int, group=None):
         self.world_size, self.rank, self.group = world_size, rank, group
         self._side = None
+        self._symm = {}
+
+    def symm_exchange(self, x: torch.Tensor):
+        """Peer-memory exchange object for [b, D] bf16 features (None when symmetric memory is unusable: CPU
+        tensors, other dtypes, or a failed rendezvous -- the NCCL P2P pipeline is used then)."""
+        from . import symm
+        if x.dtype != torch.bfloat16 or not symm.available(x.device):
+            return None
+        key = (tuple(x.shape), x.dtype)
+        if key not in self._symm:
+            try:
+                self._symm[key] = symm.SymmExchange(self.world_size, self.rank, self.group, x.device, x.shape[0],
+                                                    x.shape[1], x.dtype, torch.bfloat16)
+            except Exception as e:  # pragma: no cover  (reported once; the NCCL path still works)
+                import warnings
+                warnings.warn(f"xtag_clip_b200: symmetric-memory exchange unavailable ({e}); using NCCL P2P")
+                self._symm[key] = None
+        return self._symm[key]
 
     # -- stream helpers (no-ops for CPU tensors, so the same schedule runs under gloo in the CPU tests) --------
     def side_stream(self, device):
@@ -141,6 +159,7 @@ class _Cfg:
     comm: Optional[_Comm]
     comm_dtype: Optional[torch.dtype]
     pipeline: bool = True
+    symm: bool = True
 
 
 def _as_scale_tensor(logit_scale, device) -> torch.Tensor:
@@ -166,22 +185,34 @@ class _FusedClipLoss(torch.autograd.Function):
             off = b * r
             B = b * W
             txt_all = torch.empty((B, txt.shape[1]), dtype=txt.dtype, device=txt.device)
-            plan = cfg.comm.pipelined_gather(txt, txt_all)
-            col_part = torch.empty(B, dtype=torch.float32, device=txt.device)
+            sx = cfg.comm.symm_exchange(txt) if cfg.symm else None
+            if sx is not None:
+                sx.begin_step()
+                plan = sx.gather_pipelined(txt, txt_all)          # copy-engine pulls from peer memory
+                col_part = sx.col_buffer()
+            else:
+                plan = cfg.comm.pipelined_gather(txt, txt_all)    # batched NCCL P2P rounds
+                col_part = torch.empty(B, dtype=torch.float32, device=txt.device)
             diag = torch.empty(b, dtype=torch.float32, device=txt.device)
             row_parts = []
             for lo, hi, ev in plan:
-                if ev is not None:
-                    torch.cuda.current_stream().wait_event(ev)
+                for e in (ev if isinstance(ev, (list, tuple)) else [ev]):
+                    if e is not None:
+                        torch.cuda.current_stream().wait_event(e)
                 lab = off - lo if lo <= off < hi else -1          # only the rank's own block holds its labels
                 rp, _, _ = K.clip_fwd(img, txt_all[lo:hi], scale, lab, col_out=col_part[lo:hi], diag_out=diag)
                 row_parts.append(rp)
             row_lse = K.lse_combine(torch.stack(row_parts)) if len(row_parts) > 1 else row_parts[0]
-            side = cfg.comm.side_stream(txt.device)
-            if side is not None:
-                torch.cuda.current_stream().wait_stream(side)     # sends of `txt` done before it can be freed
-            parts = cfg.comm.all_gather_cat(col_part.reshape(1, -1))      # [W, B]
-            col_lse = K.lse_combine(parts)
+            if sx is not None:
+                sx.end_gather()
+                col_lse = sx.combine_cols(K)                      # barrier + one kernel over the W peer buffers
+                ctx.symm = (sx, sx.step)
+            else:
+                side = cfg.comm.side_stream(txt.device)
+                if side is not None:
+                    torch.cuda.current_stream().wait_stream(side)     # sends of `txt` done before it can be freed
+                parts = cfg.comm.all_gather_cat(col_part.reshape(1, -1))      # [W, B]
+                col_lse = K.lse_combine(parts)
         elif cfg.local_loss:
             off = b * r
             txt_all = cfg.comm.all_gather_cat(txt)
@@ -196,6 +227,8 @@ class _FusedClipLoss(torch.autograd.Function):
             txt_all = cfg.comm.all_gather_cat(txt)
             row_lse, col_lse, diag = K.clip_fwd(img_all, txt_all, scale, 0)
         loss = K.clip_loss(row_lse, diag, col_lse, off)
+        if not hasattr(ctx, "symm"):
+            ctx.symm = None
         ctx.cfg, ctx.off, ctx.b = cfg, off, b
         ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
         ctx.save_for_backward(img, txt, scale, row_lse, col_lse, img_all, txt_all)
@@ -218,7 +251,19 @@ class _FusedClipLoss(torch.autograd.Function):
             cdt = cfg.comm_dtype or fdt
             w = (0.5 / b, 0.5 / b, 1.0 / b)
             side = cfg.comm.side_stream(img.device) if cfg.pipeline else None
-            if need_t and need_i and cfg.pipeline:
+            sx = None
+            if ctx.symm is not None and ctx.symm[0].step == ctx.symm[1] and cdt == torch.bfloat16:
+                sx = ctx.symm[0]             # same step as the forward: its slot parity is still current
+            if need_t and need_i and sx is not None:
+                # dS + dB GEMM (partial written straight into the symmetric buffer); peers pull their blocks with
+                # the copy engines while the dA GEMM (reusing the staged dS) runs; one kernel sums the W blocks
+                _, _, ds, ws = K.clip_bwd(img, txt_all, scale, off, row_lse, col_lse, *w, g, False, True, cdt,
+                                          return_ws=True, dB_out=sx.dT_buffer())
+                sx.reduce_scatter_begin()
+                d_img, _, _ = K.clip_bwd(img, txt_all, scale, off, row_lse, col_lse, *w, g, True, False, fdt,
+                                         ws=ws, reuse_ds=True)
+                d_txt = sx.reduce_scatter_end(K).to(fdt)
+            elif need_t and need_i and cfg.pipeline:
                 # dS + dB GEMM first, reduce-scatter of the [B, D] partial on the side stream while the dA GEMM
                 # (which reuses the staged dS) runs on the main stream
                 _, d_txt_all, ds, ws = K.clip_bwd(img, txt_all, scale, off, row_lse, col_lse, *w, g, False, True, cdt,
@@ -326,6 +371,7 @@ class ClipLoss(nn.Module):
             group=None,
             comm_dtype: Optional[torch.dtype] = None,
             pipeline: bool = True,
+            symmetric_memory: bool = True,
             _kernels=None,
     ):
         super().__init__()
@@ -341,6 +387,7 @@ class ClipLoss(nn.Module):
         self._group = group
         self._comm_dtype = comm_dtype
         self._pipeline = pipeline
+        self._symm = symmetric_memory
         self._kernels = _kernels
         self._comm = None
 
@@ -392,7 +439,7 @@ class ClipLoss(nn.Module):
                 self._comm = _Comm(self.world_size, self.rank, self._group)     # keeps its side stream
             comm = self._comm
         return _Cfg(self.local_loss, self.gather_with_grad, self.rank, self.world_size, k, comm, self._comm_dtype,
-                    self._pipeline)
+                    self._pipeline, self._symm)
 
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
         if image_features.dim() != 2 or image_features.shape != text_features.shape:

@@ -1,0 +1,157 @@
+"""NVLink exchange for the sharded contrastive head over peer-mapped ("symmetric") memory.
+
+The sharded loss has one exchange step each way: forward needs every rank's text features
+and the [B] partial column log-sum-exps, backward reduces the [B, D] text-gradient partials onto their owners.  The
+reference does this with blocking NCCL collectives (loss.py:51-52 and the reduce-scatter inside
+torch.distributed.nn.all_gather's backward).  NCCL kernels need SMs, but K1/K2 are persistent kernels that occupy
+all 148 of them, so a concurrent NCCL kernel simply waits (measured: 0.3-0.9 ms stalls at 8 GPUs).  Here every bulk
+transfer is a *pull by the copy engines* from the peers' symmetric buffers -- no SMs involved -- so it overlaps with
+the tcgen05 kernels:
+
+  forward   features -> own slot; barrier; pull peer blocks chunk group by chunk group on two copy streams while
+            K1 already runs on the blocks that have landed
+  forward   K1 writes its column-LSE partials straight into a symmetric [B] buffer; barrier; one small kernel
+            reads all W peer buffers over NVLink and LSE-combines them
+  backward  the dB GEMM writes its [B, D] partial into a symmetric buffer; barrier; each rank pulls its own block
+            from the W-1 peers (copy engines, overlapped with the dA GEMM); one kernel sums the W blocks
+
+Buffers are double-buffered by step parity; together with the one barrier per use and step this orders every
+overwrite after all peers' reads of the previous use.
+torch supplies the allocation / rendezvous / barrier (torch.distributed._symmetric_memory); it is plumbing.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def available(device: torch.device) -> bool:
+    if device.type != "cuda":
+        return False
+    try:
+        import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+class SymmExchange:
+    def __init__(self, world: int, rank: int, group, device: torch.device, b: int, D: int,
+                 feat_dtype: torch.dtype, grad_dtype: torch.dtype):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.W, self.r, self.b, self.D = world, rank, b, D
+        self.B = world * b
+        self.feat_dtype, self.grad_dtype = feat_dtype, grad_dtype
+        grp = group if group is not None else dist.group.WORLD
+        self.feat = symm_mem.empty((2, b, D), dtype=feat_dtype, device=device)
+        self.h_feat = symm_mem.rendezvous(self.feat, grp)
+        self.col = symm_mem.empty((2, self.B), dtype=torch.float32, device=device)
+        self.h_col = symm_mem.rendezvous(self.col, grp)
+        self.dT = symm_mem.empty((2, self.B, D), dtype=grad_dtype, device=device)
+        self.h_dT = symm_mem.rendezvous(self.dT, grp)
+        self.peer_feat = [self.h_feat.get_buffer(p, (2, b, D), feat_dtype) for p in range(world)]
+        self.peer_dT = [self.h_dT.get_buffer(p, (2, self.B, D), grad_dtype) for p in range(world)]
+        peer_col = [self.h_col.get_buffer(p, (2, self.B), torch.float32) for p in range(world)]
+        # device arrays of peer pointers for the combine kernel, one per slot
+        self.col_ptrs = [torch.tensor([peer_col[p][s].data_ptr() for p in range(world)], dtype=torch.int64,
+                                      device=device) for s in range(2)]
+        self._keep = peer_col
+        self.pull_tmp = torch.empty((world, b, D), dtype=grad_dtype, device=device)
+        # operand pointers of the final sum, per slot: the W-1 pulled blocks and the rank's own block of its partial
+        self.sum_ptrs = [torch.tensor([self.pull_tmp[p].data_ptr() if p != rank
+                                       else self.dT[s][rank * b:(rank + 1) * b].data_ptr() for p in range(world)],
+                                      dtype=torch.int64, device=device) for s in range(2)]
+        self.s1 = torch.cuda.Stream(device=device)
+        self.s2 = torch.cuda.Stream(device=device)
+        self.step = 0
+        self.slot = 0
+
+    # ---- schedule ---------------------------------------------------------------------------------------------
+    def _blocks(self) -> List[Tuple[int, int, List[int]]]:
+        """Column blocks in consumption order: (first rank, last rank + 1, peers to pull).  The rank's own chunk
+        first (no wait), then its group partner, then the other groups of G ranks walking away from the rank."""
+        W, r = self.W, self.r
+        G = 2 if (W >= 4 and W % 2 == 0) else 1
+        NG, g0 = W // G, r // G
+        out = [(r, r + 1, [])]
+        if G == 2:
+            out.append((r ^ 1, (r ^ 1) + 1, [r ^ 1]))
+        for j in range(1, NG):
+            g = (g0 - j) % NG
+            out.append((g * G, g * G + G, list(range(g * G, g * G + G))))
+        return out
+
+    # ---- forward: feature gather ------------------------------------------------------------------------------
+    def begin_step(self):
+        self.step += 1
+        self.slot = self.step & 1
+
+    def gather_pipelined(self, x: torch.Tensor, out_all: torch.Tensor):
+        """-> [(row_lo, row_hi, event | None)]: blocks of out_all in the order they become valid."""
+        b, s = self.b, self.slot
+        cur = torch.cuda.current_stream()
+        out_all[self.r * b:(self.r + 1) * b].copy_(x)
+        self.s1.wait_stream(cur)
+        plan = []
+        with torch.cuda.stream(self.s1):
+            self.feat[s].copy_(x)
+            self.h_feat.barrier(channel=0)                  # every rank's slot s is written
+        ready = torch.cuda.Event()
+        ready.record(self.s1)
+        self.s2.wait_event(ready)
+        k = 0
+        for lo_r, hi_r, peers in self._blocks():
+            evs = []
+            for p in peers:
+                st = self.s1 if (k & 1) == 0 else self.s2
+                k += 1
+                with torch.cuda.stream(st):
+                    out_all[p * b:(p + 1) * b].copy_(self.peer_feat[p][s], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                evs.append(ev)
+            plan.append((lo_r * b, hi_r * b, evs))
+        return plan
+
+    def end_gather(self):
+        """the pull streams must be drained before the next barrier on s1 (orders the next overwrite of a slot)"""
+        self.s1.wait_stream(self.s2)
+        torch.cuda.current_stream().wait_stream(self.s1)
+
+    # ---- forward: column-LSE exchange -------------------------------------------------------------------------
+    def col_buffer(self) -> torch.Tensor:
+        return self.col[self.slot]
+
+    def combine_cols(self, K) -> torch.Tensor:
+        self.h_col.barrier(channel=1)                       # on the compute stream: all K1 launches precede it
+        return K.lse_combine_ptrs(self.col_ptrs[self.slot], self.W, self.B)
+
+    # ---- backward: reduce-scatter of the text-gradient partials -----------------------------------------------
+    def dT_buffer(self) -> torch.Tensor:
+        return self.dT[self.slot]
+
+    def reduce_scatter_begin(self):
+        """call after the dB GEMM was enqueued on the current stream; pulls run on the copy streams"""
+        b, s, r = self.b, self.slot, self.r
+        cur = torch.cuda.current_stream()
+        self.s1.wait_stream(cur)
+        with torch.cuda.stream(self.s1):
+            self.h_dT.barrier(channel=2)                    # every rank's partial is complete
+        ready = torch.cuda.Event()
+        ready.record(self.s1)
+        self.s2.wait_event(ready)
+        k = 0
+        for j in range(1, self.W):
+            p = (r + j) % self.W
+            st = self.s1 if (k & 1) == 0 else self.s2
+            k += 1
+            with torch.cuda.stream(st):
+                self.pull_tmp[p].copy_(self.peer_dT[p][s][r * b:(r + 1) * b], non_blocking=True)
+
+    def reduce_scatter_end(self, K) -> torch.Tensor:
+        cur = torch.cuda.current_stream()
+        self.s1.wait_stream(self.s2)
+        cur.wait_stream(self.s1)
+        return K.sum_ptrs_bf16(self.sum_ptrs[self.slot], self.W, (self.b, self.D))
