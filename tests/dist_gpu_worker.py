@@ -64,6 +64,25 @@ def main():
                 ref_tot = float(sum(ds))
                 if abs(tot.item() - ref_tot) > 2e-2 * abs(ref_tot) + 5e-5:
                     failures.append(f"{tag}: dscale sum {tot.item():.6e} vs {ref_tot:.6e}")
+    # CUDA-graph replay of the performance mode (captured barriers, copy-engine pulls and stream forks)
+    b, D, scale = 512, 256, 14.285714
+    g = torch.Generator().manual_seed(7)
+    I_all = torch.nn.functional.normalize(torch.randn(b * world, D, generator=g), dim=-1).bfloat16()
+    T_all = torch.nn.functional.normalize(0.3 * I_all.float() + 0.7 * torch.randn(b * world, D, generator=g), dim=-1).bfloat16()
+    mods = [xt.ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world, cuda_graph=cg)
+            for cg in (True, False)]
+    for it in range(3):
+        res = []
+        for mod in mods:
+            I = (I_all[rank * b:(rank + 1) * b].float() * (1.0 + 0.1 * it)).bfloat16().to(dev).requires_grad_(True)
+            T = T_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+            s = torch.tensor(scale, device=dev, requires_grad=True)
+            loss = mod(I, T, s)
+            loss.backward()
+            res.append((loss.detach(), I.grad, T.grad, s.grad))
+        for name, a, bb in zip(("loss", "dI", "dT", "ds"), res[0], res[1]):
+            if rel(a, bb) > 1e-5:
+                failures.append(f"cuda_graph it={it} rank={rank}: {name} differs from eager by {rel(a, bb):.2e}")
     n_fail = torch.tensor([len(failures)], device=dev)
     dist.all_reduce(n_fail)
     for f in failures:

@@ -188,3 +188,22 @@ def test_launch_counter_counts_native_kernels():
     I, T = feats(1, 256, 512)
     xt.ClipLoss()(I.bfloat16().cuda(), T.bfloat16().cuda(), 10.0)
     assert _lib.launch_count() - n0 >= 4          # tcgen05 fwd + 2 reductions + loss
+
+
+def test_cliploss_cuda_graph_replay_matches_eager():
+    """cuda_graph=True captures forward and backward once and replays them: same numbers as the eager path, for
+    fresh inputs on every call (inputs are copied into the captured step's static buffers)."""
+    graphed, eager = xt.ClipLoss(cuda_graph=True), xt.ClipLoss()
+    for it in range(4):
+        I, T = feats(100 + it, 512, 256, corr=0.3)
+        out = []
+        for mod in (graphed, eager):
+            Ic = I.bfloat16().cuda().requires_grad_(True)
+            Tc = T.bfloat16().cuda().requires_grad_(True)
+            ls = torch.tensor(2.0 + 0.2 * it, device="cuda", requires_grad=True)
+            loss = mod(Ic, Tc, ls.exp())
+            (loss * (1.0 + it)).backward()
+            out.append((loss.detach().clone(), Ic.grad.clone(), Tc.grad.clone(), ls.grad.clone()))
+        for a, b in zip(out[0], out[1]):
+            assert rel_err(a, b) < 1e-6
+    assert len(graphed._graphs) == 1

@@ -317,6 +317,79 @@ class _FusedClipLoss(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# CUDA-graph replay of one loss step (launch-bound regimes: small batches, 8-GPU shards)
+# ------------------------------------------------------------------------------------------------
+class _GraphedStep:
+    """Forward and backward of `_FusedClipLoss` captured once into two CUDA graphs (the pattern of
+    torch.cuda.make_graphed_callables): all kernels, copy-engine pulls, barriers and stream fork/joins of a step are
+    replayed with two graph launches, which removes the ~100 host-side launches per step that bound the 8-GPU shard
+    (GPU work per step < 1 ms).  Inputs are copied into static buffers; outputs are cloned out of them."""
+
+    def __init__(self, img, txt, logit_scale, cfg: "_Cfg"):
+        dev = img.device
+        self.cfg = cfg
+        self.s_img = img.detach().clone().requires_grad_(img.requires_grad)
+        self.s_txt = txt.detach().clone().requires_grad_(txt.requires_grad)
+        self.scale_is_tensor = torch.is_tensor(logit_scale)
+        if self.scale_is_tensor:
+            self.s_scale = logit_scale.detach().clone().to(dev).requires_grad_(logit_scale.requires_grad)
+        else:
+            self.s_scale = float(logit_scale)
+        self.s_g = torch.ones((), dtype=torch.float32, device=dev)
+        self.inputs = [t for t in (self.s_img, self.s_txt, self.s_scale if self.scale_is_tensor else None)
+                       if t is not None and t.requires_grad]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                                 # eager warm-up: lazy initialisations happen here
+                loss = _FusedClipLoss.apply(self.s_img, self.s_txt, self.s_scale, cfg)
+                if self.inputs:
+                    torch.autograd.grad(loss, self.inputs, self.s_g)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.pool = torch.cuda.graph_pool_handle()
+        self.fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.fwd, pool=self.pool):
+            self.s_loss = _FusedClipLoss.apply(self.s_img, self.s_txt, self.s_scale, cfg)
+        self.bwd = None
+        self.s_grads = ()
+        if self.inputs:
+            self.bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.bwd, pool=self.pool):
+                self.s_grads = torch.autograd.grad(self.s_loss, self.inputs, self.s_g)
+
+    def run_forward(self, img, txt, logit_scale):
+        self.s_img.detach().copy_(img)
+        self.s_txt.detach().copy_(txt)
+        if self.scale_is_tensor:
+            self.s_scale.detach().copy_(logit_scale.detach())
+        self.fwd.replay()
+        return self.s_loss.detach().clone()
+
+    def run_backward(self, g):
+        self.s_g.copy_(g)
+        self.bwd.replay()
+        return [t.clone() for t in self.s_grads]
+
+
+class _GraphedClipLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, txt, logit_scale, step: "_GraphedStep"):
+        ctx.step = step
+        ctx.scale_is_tensor = torch.is_tensor(logit_scale)
+        return step.run_forward(img, txt, logit_scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        step = ctx.step
+        grads = iter(step.run_backward(g))
+        d_img = next(grads) if step.s_img.requires_grad else None
+        d_txt = next(grads) if step.s_txt.requires_grad else None
+        d_s = next(grads) if (step.scale_is_tensor and step.s_scale.requires_grad) else None
+        return d_img, d_txt, d_s, None
+
+
+# ------------------------------------------------------------------------------------------------
 # reference API
 # ------------------------------------------------------------------------------------------------
 def gather_features(
@@ -372,6 +445,7 @@ class ClipLoss(nn.Module):
             comm_dtype: Optional[torch.dtype] = None,
             pipeline: bool = True,
             symmetric_memory: bool = True,
+            cuda_graph: bool = False,
             _kernels=None,
     ):
         super().__init__()
@@ -388,6 +462,8 @@ class ClipLoss(nn.Module):
         self._comm_dtype = comm_dtype
         self._pipeline = pipeline
         self._symm = symmetric_memory
+        self._cuda_graph = cuda_graph
+        self._graphs = {}
         self._kernels = _kernels
         self._comm = None
 
@@ -450,8 +526,24 @@ class ClipLoss(nn.Module):
             img, txt = image_features, text_features
         else:
             img, txt = image_features.float(), text_features.float()
-        total_loss = _FusedClipLoss.apply(img.contiguous(), txt.contiguous(), logit_scale, self._cfg())
+        img, txt = img.contiguous(), txt.contiguous()
+        if self._cuda_graph and img.is_cuda and torch.is_grad_enabled():
+            total_loss = self._forward_graphed(img, txt, logit_scale)
+        else:
+            total_loss = _FusedClipLoss.apply(img, txt, logit_scale, self._cfg())
         return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+    def _forward_graphed(self, img, txt, logit_scale):
+        """`cuda_graph=True`: one captured step per (shape, dtype, requires_grad) signature.  All ranks must take
+        the same path (the captured step contains the cross-rank barriers)."""
+        st = torch.is_tensor(logit_scale)
+        key = (tuple(img.shape), img.dtype, img.requires_grad, txt.requires_grad, st,
+               bool(st and logit_scale.requires_grad), tuple(logit_scale.shape) if st else None)
+        step = self._graphs.get(key)
+        if step is None:
+            step = _GraphedStep(img, txt, logit_scale, self._cfg())
+            self._graphs[key] = step
+        return _GraphedClipLoss.apply(img, txt, logit_scale, step)
 
 
 def create_loss(args):
