@@ -152,13 +152,15 @@ int xtag_xattn_fwd(const void* q, const void* k, const void* v, int dtype,
                    int ldq, int ldk, int ldv,
                    float softmax_scale, float dropout_p, uint64_t seed, uint64_t offset,
                    void* stream);
+/* dq [b,Lq,heads*dh], dk / dv [b,Lk,heads*dh] contiguous.  ws: scratch of at least b*heads*Lq*4 bytes
+ * (rowsum(dO*O), shared by the two backward kernels). */
 int xtag_xattn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                    const float* lse, int dtype,
                    void* dq, void* dk, void* dv,
                    int b, int Lq, int Lk, int heads, int dh,
                    int ldq, int ldk, int ldv,
                    float softmax_scale, float dropout_p, uint64_t seed, uint64_t offset,
-                   void* stream);
+                   void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5  AsymmetricLoss forward + d/dx in one pass.  Replaces AsymmetricLoss.forward

@@ -83,6 +83,13 @@ def main():
         rec = dict(kind="xattn_fwd_bf16", b=b, N=N, ms=t, gbs=b * (88 + 2 * N) * 1536 / (t * 1e-3) / 1e9)
         print(json.dumps(rec), flush=True)
         out.append(rec)
+        o, lse = K.xattn_fwd(q, k, v, 4, 1 / math.sqrt(192), 0.0, 0, 0)
+        do = torch.randn_like(o)
+        t = timeit(lambda: K.xattn_bwd(q, k, v, o, do, lse, 4, 1 / math.sqrt(192), 0.0, 0, 0))
+        # algorithmic bytes of the backward: read q,k,v,o,do ; write dq,dk,dv
+        rec = dict(kind="xattn_bwd_bf16", b=b, N=N, ms=t, gbs=b * (4 * 44 + 4 * N) * 1536 / (t * 1e-3) / 1e9)
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/sweep.jsonl", "w") as fh:
         for r in out:

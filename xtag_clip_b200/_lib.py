@@ -45,7 +45,7 @@ SIGNATURES = {
     "xtag_xattn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                               c_float, c_float, c_uint64, c_uint64, c_void_p]),
+                               c_float, c_float, c_uint64, c_uint64, c_void_p, c_size_t, c_void_p]),
     "xtag_asl_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
 }

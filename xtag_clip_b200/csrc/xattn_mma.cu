@@ -311,4 +311,387 @@ int xattn_mma_fwd(const void* q, const void* k, const void* v, void* o, float* l
   }
 }
 
+
+// =============================================================================================================
+// Backward.  Two kernels, each a forward-shaped pipeline (TMA tiles, ldmatrix, mma.sync):
+//   xattn_bwd_dq_kernel   query-major, one CTA per (sample, head): recompute S and dP = dO V^T tile by tile,
+//                         dS = P (dP*mask - delta) * scale, dQ += dS K.  Also emits delta = rowsum(dO * O).
+//   xattn_bwd_dkv_kernel  key-major, one CTA per (sample, head, 64-key tile), 16 keys per warp: S^T = K Q^T and
+//                         dP^T = V dO^T over all Lq queries, dV = Pd^T dO, dK = dS^T Q -- complete per key tile, so
+//                         there is no cross-CTA accumulation and no atomics.
+// K and V are streamed twice (once per kernel): ~3x the forward's bytes in total, still bandwidth-shaped.
+// =============================================================================================================
+template <int NCH>
+__global__ void __launch_bounds__(32 * XA_MAXW)
+xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                    const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                    const float* __restrict__ lse, __nv_bfloat16* __restrict__ dq, float* __restrict__ delta,
+                    int Lq, int Lk, int heads, float sl2, float sm_scale, float p_drop, uint64_t seed, uint64_t offset) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int nw = blockDim.x >> 5;
+  const int QROWS = 16 * nw;
+  const uint32_t q_bytes = (uint32_t)NCH * QROWS * 128;
+  const uint32_t q_pad = (q_bytes + 1023) & ~1023u;
+  constexpr uint32_t kv_chunk = XA_KT * 128;
+  constexpr uint32_t stage_bytes = 2 * NCH * kv_chunk;
+  uint8_t* Qs = smem;
+  uint8_t* dOs = smem + q_pad;
+  uint8_t* KVs = smem + 2 * q_pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(KVs + 2 * stage_bytes);
+  float* delta_s = reinterpret_cast<float*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  const int dh = NCH * 64, HD = heads * dh;
+  const int num_tiles = (Lk + XA_KT - 1) / XA_KT;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmDO);
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue_tile = [&](int t) {
+    const int st = t & 1;
+    const uint32_t fb = smem_u32(&bars[1 + st]);
+    const uint32_t base = smem_u32(KVs + st * stage_bytes);
+    mbar_arrive_expect_tx(fb, stage_bytes);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      tma_load_3d(base + c * kv_chunk, &tmK, fb, h * dh + c * 64, t * XA_KT, b);
+      tma_load_3d(base + (NCH + c) * kv_chunk, &tmV, fb, h * dh + c * 64, t * XA_KT, b);
+    }
+  };
+  if (tid == 0) {
+    const uint32_t qb = smem_u32(&bars[0]);
+    mbar_arrive_expect_tx(qb, 2 * q_bytes);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      tma_load_3d(smem_u32(Qs) + c * QROWS * 128, &tmQ, qb, h * dh + c * 64, 0, b);
+      tma_load_3d(smem_u32(dOs) + c * QROWS * 128, &tmDO, qb, h * dh + c * 64, 0, b);
+    }
+    issue_tile(0);
+  }
+  // delta_r = sum_c dO[r,c] * O[r,c] for this warp's 16 rows (straight from global memory, once)
+  for (int rr = 0; rr < 16; ++rr) {
+    const int row = warp * 16 + rr;
+    float sacc = 0.f;
+    if (row < Lq) {
+      const __nv_bfloat16* op = o + ((size_t)b * Lq + row) * HD + h * dh;
+      const __nv_bfloat16* dp = d_o + ((size_t)b * Lq + row) * HD + h * dh;
+      for (int c = lane * 2; c < dh; c += 64) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(op + c));
+        const float2 d2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp + c));
+        sacc = fmaf(a.x, d2.x, fmaf(a.y, d2.y, sacc));
+      }
+    }
+    sacc = warp_sum(sacc);
+    if (lane == 0) {
+      delta_s[row] = sacc;
+      if (row < Lq) delta[(size_t)bh * Lq + row] = sacc;
+    }
+  }
+  __syncwarp();
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const int row0 = warp * 16 + g;
+  float lse2[2], dl[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = row0 + r * 8;
+    lse2[r] = (row < Lq) ? lse[(size_t)bh * Lq + row] * kLog2e : INFINITY;
+    dl[r] = delta_s[row];
+  }
+  float qacc[NCH * 8][4];
+#pragma unroll
+  for (int i = 0; i < NCH * 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) qacc[i][j] = 0.f;
+
+  mbar_wait(smem_u32(&bars[0]), 0);
+  const uint32_t q_base = smem_u32(Qs), do_base = smem_u32(dOs);
+  const int qrow = warp * 16 + (lane & 15);
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+
+  for (int t = 0; t < num_tiles; ++t) {
+    const int st = t & 1;
+    if (tid == 0 && t + 1 < num_tiles) issue_tile(t + 1);
+    mbar_wait(smem_u32(&bars[1 + st]), (uint32_t)((t >> 1) & 1));
+    const uint32_t k_base = smem_u32(KVs + st * stage_bytes);
+    const uint32_t v_base = k_base + NCH * kv_chunk;
+    float sacc[XA_KT / 8][4], pacc[XA_KT / 8][4];
+#pragma unroll
+    for (int i = 0; i < XA_KT / 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sacc[i][j] = 0.f; pacc[i][j] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < NCH * 4; ++kk) {
+      const int c = kk >> 2, kx = (kk & 3) * 16;
+      uint32_t aq[4], ad[4];
+      ldsm_x4(q_base + c * QROWS * 128 + swz(qrow, kx + ((lane >> 4) << 3)), aq);
+      ldsm_x4(do_base + c * QROWS * 128 + swz(qrow, kx + ((lane >> 4) << 3)), ad);
+#pragma unroll
+      for (int np = 0; np < XA_KT / 16; ++np) {
+        const int krow = np * 16 + ((lane >> 4) << 3) + (lane & 7);
+        const int kcol = kx + (((lane >> 3) & 1) << 3);
+        uint32_t bk[4], bv[4];
+        ldsm_x4(k_base + c * kv_chunk + swz(krow, kcol), bk);
+        ldsm_x4(v_base + c * kv_chunk + swz(krow, kcol), bv);
+        mma_bf16(sacc[2 * np], aq, bk[0], bk[1]);
+        mma_bf16(sacc[2 * np + 1], aq, bk[2], bk[3]);
+        mma_bf16(pacc[2 * np], ad, bv[0], bv[1]);
+        mma_bf16(pacc[2 * np + 1], ad, bv[2], bv[3]);
+      }
+    }
+    const int key0 = t * XA_KT;
+#pragma unroll
+    for (int i = 0; i < XA_KT / 8; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = key0 + i * 8 + t4 * 2 + (j & 1);
+        const int r = j >> 1;
+        float p = (key < Lk) ? fast_exp2(fmaf(sacc[i][j], sl2, -lse2[r])) : 0.f;
+        float m = 1.f;
+        if (p_drop > 0.f) {
+          const uint64_t idx = ((uint64_t)bh * Lq + (row0 + r * 8)) * Lk + key;
+          m = philox_keep(seed, offset, idx, p_drop) ? keep_scale : 0.f;
+        }
+        sacc[i][j] = p * (pacc[i][j] * m - dl[r]) * sm_scale;        // dS (w.r.t. q.k before the 1/sqrt(dh) scale)
+      }
+    }
+#pragma unroll
+    for (int ks = 0; ks < XA_KT / 16; ++ks) {
+      uint32_t a[4];
+      a[0] = pack_bf16(sacc[2 * ks][0], sacc[2 * ks][1]);
+      a[1] = pack_bf16(sacc[2 * ks][2], sacc[2 * ks][3]);
+      a[2] = pack_bf16(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
+      a[3] = pack_bf16(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
+#pragma unroll
+      for (int dn = 0; dn < NCH * 4; ++dn) {
+        const int krow = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+        const int kcol = dn * 16 + ((lane >> 4) << 3);
+        uint32_t bb[4];
+        ldsm_x4_t(k_base + (kcol >> 6) * kv_chunk + swz(krow, kcol & 63), bb);
+        mma_bf16(qacc[2 * dn], a, bb[0], bb[1]);
+        mma_bf16(qacc[2 * dn + 1], a, bb[2], bb[3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = row0 + r * 8;
+    if (row >= Lq) continue;
+    __nv_bfloat16* orow = dq + ((size_t)b * Lq + row) * HD + h * dh;
+#pragma unroll
+    for (int i = 0; i < NCH * 8; ++i)
+      *reinterpret_cast<uint32_t*>(orow + i * 8 + t4 * 2) = pack_bf16(qacc[i][2 * r], qacc[i][2 * r + 1]);
+  }
+}
+
+constexpr int XA_KTB = 64;       // keys per CTA in the dK/dV kernel (4 warps x 16 keys)
+
+template <int NCH, int NQT>      // NQT = number of 16-row query tiles (Lq <= 16 * NQT)
+__global__ void __launch_bounds__(128)
+xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                     const float* __restrict__ lse, const float* __restrict__ delta,
+                     __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv,
+                     int Lq, int Lk, int heads, int tiles_per_bh, float sl2, float sm_scale, float p_drop, uint64_t seed,
+                     uint64_t offset) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int QROWS = 16 * NQT;
+  constexpr uint32_t q_bytes = (uint32_t)NCH * QROWS * 128;
+  constexpr uint32_t q_pad = (q_bytes + 1023) & ~1023u;
+  constexpr uint32_t kv_chunk = XA_KTB * 128;
+  uint8_t* Qs = smem;
+  uint8_t* dOs = smem + q_pad;
+  uint8_t* Ks = smem + 2 * q_pad;
+  uint8_t* Vs = Ks + NCH * kv_chunk;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + NCH * kv_chunk);
+  float* lse2_s = reinterpret_cast<float*>(bars + 2);
+  float* delta_s = lse2_s + QROWS;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.x / tiles_per_bh, kt = blockIdx.x % tiles_per_bh;
+  const int b = bh / heads, h = bh % heads;
+  const int dh = NCH * 64, HD = heads * dh;
+  const int key_base = kt * XA_KTB;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmDO);
+    mbar_init(smem_u32(&bars[0]), 1);
+    fence_barrier_init();
+  }
+  for (int i = tid; i < QROWS; i += blockDim.x) {
+    lse2_s[i] = (i < Lq) ? lse[(size_t)bh * Lq + i] * kLog2e : INFINITY;      // +inf: padded queries get P = 0
+    delta_s[i] = (i < Lq) ? delta[(size_t)bh * Lq + i] : 0.f;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t fb = smem_u32(&bars[0]);
+    mbar_arrive_expect_tx(fb, 2 * q_bytes + 2 * NCH * kv_chunk);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      tma_load_3d(smem_u32(Qs) + c * QROWS * 128, &tmQ, fb, h * dh + c * 64, 0, b);
+      tma_load_3d(smem_u32(dOs) + c * QROWS * 128, &tmDO, fb, h * dh + c * 64, 0, b);
+      tma_load_3d(smem_u32(Ks) + c * kv_chunk, &tmK, fb, h * dh + c * 64, key_base, b);
+      tma_load_3d(smem_u32(Vs) + c * kv_chunk, &tmV, fb, h * dh + c * 64, key_base, b);
+    }
+  }
+  mbar_wait(smem_u32(&bars[0]), 0);
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const uint32_t q_base = smem_u32(Qs), do_base = smem_u32(dOs), k_base = smem_u32(Ks), v_base = smem_u32(Vs);
+  const int krow_a = warp * 16 + (lane & 15);                    // A-operand row (key) supplied by this lane
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+
+  // S^T = K_w Q^T and dP^T = V_w dO^T : 16 keys x QROWS queries
+  float st[2 * NQT][4], pt[2 * NQT][4];
+#pragma unroll
+  for (int i = 0; i < 2 * NQT; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { st[i][j] = 0.f; pt[i][j] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < NCH * 4; ++kk) {
+    const int c = kk >> 2, kx = (kk & 3) * 16;
+    uint32_t ak[4], av[4];
+    ldsm_x4(k_base + c * kv_chunk + swz(krow_a, kx + ((lane >> 4) << 3)), ak);
+    ldsm_x4(v_base + c * kv_chunk + swz(krow_a, kx + ((lane >> 4) << 3)), av);
+#pragma unroll
+    for (int np = 0; np < NQT; ++np) {
+      const int qr = np * 16 + ((lane >> 4) << 3) + (lane & 7);
+      const int qc = kx + (((lane >> 3) & 1) << 3);
+      uint32_t bq[4], bd[4];
+      ldsm_x4(q_base + c * QROWS * 128 + swz(qr, qc), bq);
+      ldsm_x4(do_base + c * QROWS * 128 + swz(qr, qc), bd);
+      mma_bf16(st[2 * np], ak, bq[0], bq[1]);
+      mma_bf16(st[2 * np + 1], ak, bq[2], bq[3]);
+      mma_bf16(pt[2 * np], av, bd[0], bd[1]);
+      mma_bf16(pt[2 * np + 1], av, bd[2], bd[3]);
+    }
+  }
+  // elementwise: rows = keys (g, g+8), columns = queries
+#pragma unroll
+  for (int i = 0; i < 2 * NQT; ++i) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int qi = i * 8 + t4 * 2 + (j & 1);
+      const int key = key_base + warp * 16 + g + ((j >> 1) << 3);
+      const float p = fast_exp2(fmaf(st[i][j], sl2, -lse2_s[qi]));
+      float m = 1.f;
+      if (p_drop > 0.f) {
+        const uint64_t idx = ((uint64_t)bh * Lq + qi) * Lk + key;
+        m = (qi < Lq && key < Lk && philox_keep(seed, offset, idx, p_drop)) ? keep_scale : 0.f;
+      }
+      st[i][j] = p * (pt[i][j] * m - delta_s[qi]) * sm_scale;    // dS^T
+      pt[i][j] = p * m;                                          // dropped probabilities Pd^T
+    }
+  }
+  const int key_lo = key_base + warp * 16 + g;
+  // two passes over the head dimension with one accumulator set: dV = Pd^T dO, then dK = dS^T Q
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    float acc[NCH * 8][4];
+#pragma unroll
+    for (int i = 0; i < NCH * 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const uint32_t b_base = pass == 0 ? do_base : q_base;
+#pragma unroll
+    for (int ks = 0; ks < NQT; ++ks) {
+      uint32_t a[4];
+      if (pass == 0) {
+        a[0] = pack_bf16(pt[2 * ks][0], pt[2 * ks][1]);         a[1] = pack_bf16(pt[2 * ks][2], pt[2 * ks][3]);
+        a[2] = pack_bf16(pt[2 * ks + 1][0], pt[2 * ks + 1][1]); a[3] = pack_bf16(pt[2 * ks + 1][2], pt[2 * ks + 1][3]);
+      } else {
+        a[0] = pack_bf16(st[2 * ks][0], st[2 * ks][1]);         a[1] = pack_bf16(st[2 * ks][2], st[2 * ks][3]);
+        a[2] = pack_bf16(st[2 * ks + 1][0], st[2 * ks + 1][1]); a[3] = pack_bf16(st[2 * ks + 1][2], st[2 * ks + 1][3]);
+      }
+#pragma unroll
+      for (int dn = 0; dn < NCH * 4; ++dn) {
+        const int qr = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+        const int dc = dn * 16 + ((lane >> 4) << 3);
+        uint32_t bb[4];
+        ldsm_x4_t(b_base + (dc >> 6) * QROWS * 128 + swz(qr, dc & 63), bb);
+        mma_bf16(acc[2 * dn], a, bb[0], bb[1]);
+        mma_bf16(acc[2 * dn + 1], a, bb[2], bb[3]);
+      }
+    }
+    __nv_bfloat16* outp = pass == 0 ? dv : dk;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int key = key_lo + r * 8;
+      if (key >= Lk) continue;
+      __nv_bfloat16* orow = outp + ((size_t)b * Lk + key) * HD + h * dh;
+#pragma unroll
+      for (int i = 0; i < NCH * 8; ++i)
+        *reinterpret_cast<uint32_t*>(orow + i * 8 + t4 * 2) = pack_bf16(acc[i][2 * r], acc[i][2 * r + 1]);
+    }
+  }
+}
+
+template <int NCH>
+static int launch_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                      void* dq, void* dk, void* dv, float* delta, int b, int Lq, int Lk, int heads, int ldq, int ldk,
+                      int ldv, float sm_scale, float p, uint64_t seed, uint64_t offset, cudaStream_t st) {
+  const int dh = NCH * 64, HD = heads * dh;
+  const int nw = (Lq + 15) / 16;
+  const float sl2 = sm_scale * kLog2e;
+  CUtensorMap tq, tdo, tk, tv, tk2, tv2;
+  int rc;
+  if ((rc = xa_make_tmap(&tq, q, b, Lq, HD, ldq, 16 * nw))) return rc;
+  if ((rc = xa_make_tmap(&tdo, d_o, b, Lq, HD, HD, 16 * nw))) return rc;
+  if ((rc = xa_make_tmap(&tk, k, b, Lk, HD, ldk, XA_KT))) return rc;
+  if ((rc = xa_make_tmap(&tv, v, b, Lk, HD, ldv, XA_KT))) return rc;
+  if ((rc = xa_make_tmap(&tk2, k, b, Lk, HD, ldk, XA_KTB))) return rc;
+  if ((rc = xa_make_tmap(&tv2, v, b, Lk, HD, ldv, XA_KTB))) return rc;
+  {
+    const size_t q_pad = ((size_t)NCH * 16 * nw * 128 + 1023) & ~(size_t)1023;
+    const size_t smem = 1024 + 2 * q_pad + 2 * (2 * NCH * XA_KT * 128) + 64 + 16 * nw * 4;
+    XTAG_CUDA(cudaFuncSetAttribute(xattn_bwd_dq_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    xattn_bwd_dq_kernel<NCH><<<b * heads, 32 * nw, smem, st>>>(tq, tk, tv, tdo, (const __nv_bfloat16*)o,
+                                                               (const __nv_bfloat16*)d_o, lse, (__nv_bfloat16*)dq, delta,
+                                                               Lq, Lk, heads, sl2, sm_scale, p, seed, offset);
+    XTAG_CHECK_LAUNCH();
+  }
+  {
+    const int tiles = (Lk + XA_KTB - 1) / XA_KTB;
+    auto launch = [&](auto kern, int nqt) -> int {
+      const size_t q_pad = ((size_t)NCH * 16 * nqt * 128 + 1023) & ~(size_t)1023;
+      const size_t smem = 1024 + 2 * q_pad + 2 * NCH * XA_KTB * 128 + 64 + 2 * 16 * nqt * 4;
+      XTAG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<b * heads * tiles, 128, smem, st>>>(tq, tk2, tv2, tdo, lse, delta, (__nv_bfloat16*)dk, (__nv_bfloat16*)dv, Lq,
+                                                 Lk, heads, tiles, sl2, sm_scale, p, seed, offset);
+      XTAG_CHECK_LAUNCH();
+      return XTAG_OK;
+    };
+    switch (nw) {
+      case 1: rc = launch(xattn_bwd_dkv_kernel<NCH, 1>, 1); break;
+      case 2: rc = launch(xattn_bwd_dkv_kernel<NCH, 2>, 2); break;
+      case 3: rc = launch(xattn_bwd_dkv_kernel<NCH, 3>, 3); break;
+      default: rc = launch(xattn_bwd_dkv_kernel<NCH, 4>, 4); break;
+    }
+    if (rc) return rc;
+  }
+  return XTAG_OK;
+}
+
+// delta_ws: caller scratch of b*heads*Lq floats
+int xattn_mma_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                  void* dq, void* dk, void* dv, float* delta_ws, int b, int Lq, int Lk, int heads, int dh, int ldq, int ldk,
+                  int ldv, float sm_scale, float p_drop, uint64_t seed, uint64_t offset, cudaStream_t st) {
+  switch (dh / 64) {
+    case 1: return launch_bwd<1>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+    case 2: return launch_bwd<2>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+    case 3: return launch_bwd<3>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+    default: return launch_bwd<4>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+  }
+}
+
 }  // namespace xtag

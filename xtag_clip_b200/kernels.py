@@ -207,10 +207,11 @@ class CudaKernels:
         dq = torch.empty((b, Lq, H), dtype=q.dtype, device=q.device)
         dk = torch.empty((b, Lk, H), dtype=q.dtype, device=q.device)
         dv = torch.empty((b, Lk, H), dtype=q.dtype, device=q.device)
+        ws = torch.empty(b * heads * Lq, dtype=torch.float32, device=q.device)
         check(self.lib.xtag_xattn_bwd(_p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _dt(q), _p(dq), _p(dk), _p(dv),
                                       b, Lq, Lk, heads, dh, q.stride(1), k.stride(1), v.stride(1),
-                                      float(softmax_scale), float(dropout_p), int(seed), int(offset), _stream()),
-              "xtag_xattn_bwd")
+                                      float(softmax_scale), float(dropout_p), int(seed), int(offset),
+                                      _p(ws), ws.numel() * 4, _stream()), "xtag_xattn_bwd")
         return dq, dk, dv
 
     # ---- K5 ----------------------------------------------------------------------------------
