@@ -322,8 +322,12 @@ def run_ours(args):
         if dom_tag is not None:
             recs = per[dom_tag]
             ach = sum(r[1] for r in recs) / (sum(r[0] for r in recs) * 1e-3) / 1e12
+            # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (1 GPU, this config)
+            traffic = 3.32e9 if (dom_tag == 2 and world == 1 and B == GLOBAL_BATCH and D == DIM) else None
             roofline = dict(bound="tensor", kernel=names.get(dom_tag), achieved=ach, peak=peaks["sustained"],
-                            unit="TFLOP/s", frac=ach / peaks["sustained"], traffic=None,
+                            unit="TFLOP/s", frac=ach / peaks["sustained"], traffic=traffic,
+                            traffic_src="profiles/r1_ncu_full_final_raw.csv (dram__bytes_read+write per launch; "
+                                        "algorithmic 2.27e9)" if traffic else None,
                             peak_kind=f"bf16 sustained, {peaks['src']} (kernel timed inside a long step); "
                                       f"burst peak {peaks['burst']}",
                             flops_per_launch=sum(r[1] for r in recs) / len(recs),
