@@ -210,7 +210,63 @@ def main():
     golden_clip_w1()
     golden_clip_dist()
     golden_tag_head()
+    golden_config1()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--config1" not in sys.argv:
     main()
+
+
+def golden_config1():
+    """BASELINE config 1: the reference's own ViT-B-32 XTag model (random init, seed 0), batch 16 of 224x224 images
+    and 77-token captions on CPU: encoders (reference code, out of scope) -> normalised features + ViT tokens, then
+    the hot path exactly as the training loop runs it (train_other_simple.py:125-135): tag_forward, ClipLoss, ASL.
+    The fixture stores the encoder outputs (the hot path's inputs) and the reference's head outputs / gradients."""
+    oc = ref_shim.load_ref_open_clip()
+    torch.manual_seed(0)
+    with ref_shim._cwd(os.path.join(ref_shim.REF_SRC, "open_clip")):
+        model = oc.create_model("ViT-B-32", pretrained=None, precision="fp32", device="cpu", output_dict=True)
+    model.eval()
+    # deterministic tag-head weights (the 54 MB of random init cannot be stored): same generator as the tests use
+    params = make_tag_params(50, 512, gain=4.0, dtype=torch.float32)
+    sd = model.state_dict()
+    sd.update(params)
+    model.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(123)
+    images = torch.randn(16, 3, 224, 224, generator=g)
+    text = torch.randint(1, 49405, (16, 77), generator=g)
+    eot = torch.randint(5, 77, (16,), generator=g)
+    for i in range(16):
+        text[i, eot[i]] = 49407
+        text[i, eot[i] + 1:] = 0
+    additional = (torch.rand(16, 22, generator=g) > 0.7).float()
+    with torch.no_grad():
+        image_features, tokens = model.encode_image(images, normalize=True)
+        text_features, _ = model.encode_text(text, normalize=True)
+    image_features = image_features.clone().requires_grad_(True)
+    text_features = text_features.clone().requires_grad_(True)
+    tokens = tokens.clone().requires_grad_(True)
+    logit_scale = model.logit_scale.detach().exp().clone().requires_grad_(True)
+    ref_loss = ref_shim.load_ref_loss()
+    asl = ref_shim.load_ref_asl()
+    tag_logits = model.tag_forward(tokens)
+    closs = ref_loss.ClipLoss()(image_features, text_features, logit_scale)
+    tloss = asl.AsymmetricLoss()(tag_logits, additional.repeat(1, 2))
+    (closs + tloss).backward()
+    words = model.prepare_control_words(tag_logits.detach())
+    np.savez_compressed(
+        os.path.join(OUT, "config1.npz"),
+        image_features=image_features.detach().numpy(), text_features=text_features.detach().numpy(),
+        tokens=tokens.detach().numpy().astype(np.float32), additional=additional.numpy(),
+        logit_scale=logit_scale.detach().numpy(), tag_logits=tag_logits.detach().numpy(),
+        contrastive_loss=closs.detach().numpy(), tag_loss=tloss.detach().numpy(),
+        d_image_features=image_features.grad.numpy(), d_text_features=text_features.grad.numpy(),
+        d_tokens_norm=np.asarray(tokens.grad.norm().item()), d_tokens_head=tokens.grad[:2, :4, :16].numpy().copy(),
+        d_logit_scale=logit_scale.grad.numpy(), words=np.asarray(words), tag_list=np.asarray(model.tag_list),
+        n_params=np.asarray(sum(p.numel() for p in model.parameters())))
+    print("config1.npz", float(closs), float(tloss), words[:2])
+
+
+if __name__ == "__main__" and "--config1" in sys.argv:
+    os.makedirs(OUT, exist_ok=True)
+    golden_config1()

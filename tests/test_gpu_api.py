@@ -207,3 +207,36 @@ def test_cliploss_cuda_graph_replay_matches_eager():
         for a, b in zip(out[0], out[1]):
             assert rel_err(a, b) < 1e-6
     assert len(graphed._graphs) == 1
+
+
+def test_config1_heads_on_reference_encoder_outputs(golden_dir):
+    """BASELINE config 1: the hot path on the outputs of the reference's own ViT-B-32 encoders (batch 16, CPU fp32 run
+    of the unmodified reference, tests/golden/config1.npz): ClipLoss, tag head + AsymmetricLoss and their gradients."""
+    g = np.load(os.path.join(golden_dir, "config1.npz"))
+    I = torch.from_numpy(g["image_features"]).cuda().requires_grad_(True)
+    T = torch.from_numpy(g["text_features"]).cuda().requires_grad_(True)
+    s = torch.tensor(float(g["logit_scale"]), device="cuda", requires_grad=True)
+    tok = torch.from_numpy(g["tokens"]).cuda().requires_grad_(True)
+    head = xt.TagHead(512, tag_list=list(g["tag_list"])).cuda()
+    head.load_state_dict(make_tag_params(50, 512, gain=4.0, dtype=torch.float32), strict=True)
+    head.eval()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    logits = head.tag_forward(tok)
+    closs = xt.ClipLoss()(I, T, s, output_dict=True)["contrastive_loss"]
+    tloss = xt.AsymmetricLoss()(logits, torch.from_numpy(g["additional"]).repeat(1, 2))
+    (closs + tloss).backward()
+    assert rel_err(closs, g["contrastive_loss"]) < 1e-5
+    assert rel_err(I.grad, g["d_image_features"]) < 2e-5 and rel_err(T.grad, g["d_text_features"]) < 2e-5
+    assert rel_err(logits, g["tag_logits"]) < 1e-4
+    assert rel_err(tloss, g["tag_loss"]) < 1e-4
+    assert rel_err(tok.grad[:2, :4, :16], g["d_tokens_head"]) < 1e-3
+    assert abs(tok.grad.norm().item() - float(g["d_tokens_norm"])) < 1e-3 * float(g["d_tokens_norm"])
+    assert head.prepare_control_words(logits.detach()) == list(g["words"])
+    # the same step under bf16 autocast, as the reference trains (--precision amp_bf16): BASELINE bf16 bars
+    I2 = torch.from_numpy(g["image_features"]).cuda().bfloat16().requires_grad_(True)
+    T2 = torch.from_numpy(g["text_features"]).cuda().bfloat16().requires_grad_(True)
+    l2 = xt.ClipLoss()(I2, T2, torch.tensor(float(g["logit_scale"]), device="cuda"))
+    l2.backward()
+    ref = oracle.clip_loss_closed_form(I2.detach().double().cpu(), T2.detach().double().cpu(),
+                                       torch.tensor(float(g["logit_scale"]), dtype=torch.float64))
+    assert rel_err(l2, ref[0]) < 1e-3 and rel_err(I2.grad, ref[1]) < 2e-2 and rel_err(T2.grad, ref[2]) < 2e-2

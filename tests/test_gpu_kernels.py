@@ -191,7 +191,8 @@ def test_lse_combine(K):
 # ---------------------------------------------------------------------------------------------- K4
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("b,Lq,Lk,heads,dh", [(3, 44, 50, 4, 192), (2, 44, 197, 4, 192), (2, 44, 257, 4, 192),
-                                              (2, 7, 5, 2, 16), (1, 44, 64, 4, 192)])
+                                              (2, 7, 5, 2, 16), (1, 44, 64, 4, 192), (2, 16, 33, 2, 64),
+                                              (2, 30, 100, 3, 128), (1, 64, 130, 2, 256), (2, 1, 1, 4, 192)])
 def test_xattn(K, MK, dtype, b, Lq, Lk, heads, dh):
     g = torch.Generator().manual_seed(b * 100 + Lk)
     H = heads * dh

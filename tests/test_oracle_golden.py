@@ -123,3 +123,29 @@ def test_tag_head_golden(golden_dir):
         tag_list = list(g[pre + "tag_list"])
         words = [",".join(tag_list[i] for i in row) for row in idx.tolist()]
         assert words == list(g[pre + "words"])
+
+
+def test_config1_golden(golden_dir):
+    """BASELINE config 1 (reference ViT-B-32 XTag model, batch 16, CPU fp32): the oracle reproduces the reference's
+    head outputs from the reference's encoder outputs."""
+    g = _load(golden_dir, "config1.npz")
+    assert int(g["n_params"]) > 150_000_000                      # the full 178.5 M-parameter model produced this
+    I = torch.from_numpy(g["image_features"]).double().requires_grad_(True)
+    T = torch.from_numpy(g["text_features"]).double().requires_grad_(True)
+    s = torch.tensor(float(g["logit_scale"]), dtype=torch.float64, requires_grad=True)
+    tok = torch.from_numpy(g["tokens"]).double().requires_grad_(True)
+    params = make_tag_params(50, 512, gain=4.0, dtype=torch.float64)
+    logits = oracle.tag_head_forward(tok, params)
+    closs = oracle.clip_loss_single(I, T, s)
+    tloss = oracle.asymmetric_loss(logits, torch.from_numpy(g["additional"]).double().repeat(1, 2))
+    (closs + tloss).backward()
+    tol = dict(rtol=2e-4, atol=2e-5)                             # the reference ran in fp32
+    np.testing.assert_allclose(logits.detach().numpy(), g["tag_logits"], **tol)
+    np.testing.assert_allclose(closs.item(), g["contrastive_loss"], rtol=1e-5)
+    np.testing.assert_allclose(tloss.item(), g["tag_loss"], rtol=1e-4)
+    np.testing.assert_allclose(I.grad.numpy(), g["d_image_features"], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(T.grad.numpy(), g["d_text_features"], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(tok.grad[:2, :4, :16].numpy(), g["d_tokens_head"], rtol=2e-3, atol=1e-5)
+    idx = oracle.control_word_indices(logits.detach())
+    tl = list(g["tag_list"])
+    assert [",".join(tl[i] for i in row) for row in idx.tolist()] == list(g["words"])

@@ -541,8 +541,15 @@ class ClipLoss(nn.Module):
                bool(st and logit_scale.requires_grad), tuple(logit_scale.shape) if st else None)
         step = self._graphs.get(key)
         if step is None:
-            step = _GraphedStep(img, txt, logit_scale, self._cfg())
+            try:
+                step = _GraphedStep(img, txt, logit_scale, self._cfg())
+            except Exception as e:      # capture refused (e.g. an op that is illegal under capture): stay eager
+                import warnings
+                warnings.warn(f"xtag_clip_b200: CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly")
+                step = False
             self._graphs[key] = step
+        if step is False:
+            return _FusedClipLoss.apply(img, txt, logit_scale, self._cfg())
         return _GraphedClipLoss.apply(img, txt, logit_scale, step)
 
 
