@@ -193,8 +193,11 @@ def test_launch_counter_counts_native_kernels():
 def test_cliploss_cuda_graph_replay_matches_eager():
     """cuda_graph=True captures forward and backward once and replays them: same numbers as the eager path, for
     fresh inputs on every call (inputs are copied into the captured step's static buffers)."""
+    from xtag_clip_b200 import _lib
     graphed, eager = xt.ClipLoss(cuda_graph=True), xt.ClipLoss()
+    counts = []
     for it in range(4):
+        counts.append(_lib.launch_count())
         I, T = feats(100 + it, 512, 256, corr=0.3)
         out = []
         for mod in (graphed, eager):
@@ -207,6 +210,10 @@ def test_cliploss_cuda_graph_replay_matches_eager():
         for a, b in zip(out[0], out[1]):
             assert rel_err(a, b) < 1e-6
     assert len(graphed._graphs) == 1
+    # replays are credited to the library's launch counter (bench.py's gpu_launches): every iteration launches the
+    # same number of library kernels through the graph as through the eager module
+    per_iter = [b - a for a, b in zip(counts, counts[1:])]
+    assert per_iter[1] == per_iter[2] > 10 and per_iter[1] % 2 == 0
 
 
 def test_config1_heads_on_reference_encoder_outputs(golden_dir):

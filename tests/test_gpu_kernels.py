@@ -209,7 +209,11 @@ def test_xattn(K, MK, dtype, b, Lq, Lk, heads, dh):
     do = torch.randn(b, Lq, H, generator=g).to(dtype)
     dq, dk, dv = K.xattn_bwd(qc, kc, vc, o, do.cuda(), lse, heads, sc, 0.0, 0, 0)
     dqm, dkm, dvm = MK.xattn_bwd(q, k, v, om, do, lsem, heads, sc, 0.0, 0, 0)
-    assert rel_err(dq, dqm) < tol * 2 and rel_err(dk, dkm) < tol * 2 and rel_err(dv, dvm) < tol * 2
+    def close(a, b):            # absolute floor: with a single key the softmax is constant and dq = dk = 0 exactly
+        a64, b64 = a.detach().double().cpu(), b.detach().double().cpu()
+        return float((a64 - b64).abs().max()) <= 2 * tol * float(b64.abs().max()) + 1e-5
+
+    assert close(dq, dqm) and close(dk, dkm) and close(dv, dvm)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

@@ -75,5 +75,16 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
 
 
+_replayed = 0
+
+
+def note_replayed(n: int) -> None:
+    """kernels of this library executed by a CUDA-graph replay (they were counted once, at capture)"""
+    global _replayed
+    _replayed += int(n)
+
+
 def launch_count() -> int:
-    return int(load().xtag_launch_count())
+    """kernels of libxtag_b200 launched by this process: direct launches (counted inside the library) plus the
+    library's kernel nodes of every CUDA-graph replay"""
+    return int(load().xtag_launch_count()) + _replayed

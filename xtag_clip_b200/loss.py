@@ -347,16 +347,23 @@ class _GraphedStep:
                     torch.autograd.grad(loss, self.inputs, self.s_g)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(dev)
+        from . import _lib
+        self._lib = _lib
         self.pool = torch.cuda.graph_pool_handle()
         self.fwd = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         with torch.cuda.graph(self.fwd, pool=self.pool):
             self.s_loss = _FusedClipLoss.apply(self.s_img, self.s_txt, self.s_scale, cfg)
+        self.n_fwd = _lib.launch_count() - n0          # library kernels recorded into the forward graph
         self.bwd = None
         self.s_grads = ()
+        self.n_bwd = 0
         if self.inputs:
             self.bwd = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
             with torch.cuda.graph(self.bwd, pool=self.pool):
                 self.s_grads = torch.autograd.grad(self.s_loss, self.inputs, self.s_g)
+            self.n_bwd = _lib.launch_count() - n0
 
     def run_forward(self, img, txt, logit_scale):
         self.s_img.detach().copy_(img)
@@ -364,11 +371,13 @@ class _GraphedStep:
         if self.scale_is_tensor:
             self.s_scale.detach().copy_(logit_scale.detach())
         self.fwd.replay()
+        self._lib.note_replayed(self.n_fwd)
         return self.s_loss.detach().clone()
 
     def run_backward(self, g):
         self.s_g.copy_(g)
         self.bwd.replay()
+        self._lib.note_replayed(self.n_bwd)
         return [t.clone() for t in self.s_grads]
 
 
