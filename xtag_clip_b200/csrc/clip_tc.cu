@@ -8,8 +8,9 @@
 //                           (max,sum-exp) partials per row and per column and picks the label logit
 //                           (reference src/open_clip/loss.py:116-124 + F.cross_entropy at :134-137)
 //   EPI_DS     K2 backward  S recomputed, dS = g*(w_row*softmax_row + w_col*softmax_col - w_diag*1[label])
-//                           written once as bf16 in both orientations (dS and dS^T) + d(logit_scale) partials
-//   EPI_STORE  plain GEMM   C = alpha*acc (fp32 or bf16): dA = scale*dS*Bm and dB = scale*dS^T*A
+//                           written once as bf16 by per-warp TMA tile stores + d(logit_scale) partials
+//   EPI_STORE  plain GEMM   C = alpha*acc (fp32 or bf16): dA = scale*dS*Bm and dB = scale*dS^T*A, with dS and the
+//                           features read in place (MN-major UMMA operands)
 //
 // Pipeline per CTA (384 threads, 1 CTA / SM, grid = #SMs, static tile schedule with grouped rasterisation):
 //   warp 0      TMA producer  : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a 4-stage smem ring
@@ -57,8 +58,7 @@ struct EpiParams {
   float w_row, w_col, w_diag;
   const float* grad_out;  // device scalar
   __nv_bfloat16* dS;      // [M][ldds]
-  __nv_bfloat16* dST;     // [N][lddst]   (may be null)
-  int ldds, lddst;
+  int ldds;
   float* dscale_part;     // [grid * kEpiWarps]
   // EPI_STORE
   void* C;
@@ -288,7 +288,7 @@ __device__ __forceinline__ float ds_tile(const EpiParams& ep, const CUtensorMap*
     // ---- store: 32 rows x 64 B of bf16 through shared memory and one TMA tile store per warp and chunk.
     // Direct STG would write 16 B per 128-B line per instruction (32 L2 requests per warp instruction, measured as
     // the kernel's dominant stall); the TMA store issues full 64-B row segments and clips ragged edges itself.
-    if (ep.dST == nullptr) {
+    {
       if (lane == 0) tma_store_wait_read();                 // previous tile store has drained this buffer
       __syncwarp();
 #pragma unroll
@@ -306,15 +306,6 @@ __device__ __forceinline__ float ds_tile(const EpiParams& ep, const CUtensorMap*
         tma_store_2d(tmC, ostage, c0, row_blk);
         tma_store_commit();
       }
-    } else if (row_ok) {
-      // A/B-testing layout (XTAG_TC_BWD_LAYOUT=transposed): direct stores of dS and dS^T
-      __nv_bfloat16* dst = ep.dS + (size_t)gi * ep.ldds + c0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (FULL || c0 + j < N) {
-          dst[j] = __float2bfloat16_rn(d[j]);
-          ep.dST[(size_t)(c0 + j) * ep.lddst + gi] = __float2bfloat16_rn(d[j]);
-        }
     }
   }
   return (dsp[0] + dsp[1]) + (dsp[2] + dsp[3]);
@@ -652,7 +643,6 @@ int tc_grid_for(int M, int N) {
 
 int launch_lse_reduce(const float* parts, int P, int n, float in_mul, float out_mul, float* out, cudaStream_t st);
 int launch_sum_into(const float* parts, int n, float* out, cudaStream_t st);
-int launch_transpose(const void* in, void* out, int dtype, int rows, int cols, cudaStream_t st);
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -679,76 +669,36 @@ int tc_clip_fwd(const void* A, const void* Bm, int M, int N, int D, const float*
   return launch_lse_reduce(ep.col_part, num_m, N, 1.f, kLn2, col_lse, st);
 }
 
-// Backward workspace.  Default ("mn") layout: dS [M][Np] bf16 only -- the two gradient GEMMs read dS and the
-// features in place through MN-major UMMA descriptors.  XTAG_TC_BWD_LAYOUT=transposed (A/B testing only) also
-// stages dS^T [N][Mp] and transposed features so that every operand is K-major.
+// Backward workspace: dS [M][Np] bf16 (Np = N padded to 8 so rows stay 16-byte multiples) + d(logit_scale) partials.
+// The two gradient GEMMs read dS and the features in place through MN-major UMMA descriptors.
 struct BwdLayout {
-  size_t Mp, Np, off_ds, off_dst, off_at, off_bt, off_part, total;
+  size_t Np, off_ds, off_part, total;
 };
-static bool bwd_transposed_layout() {
-  static int cached = -1;
-  if (cached < 0) {
-    const char* e = getenv("XTAG_TC_BWD_LAYOUT");
-    cached = (e && e[0] == 't') ? 1 : 0;
-  }
-  return cached == 1;
-}
 static BwdLayout bwd_layout(int M, int N, int D) {
+  (void)D;
   BwdLayout L;
-  const bool tr = bwd_transposed_layout();
-  L.Mp = ((size_t)M + 7) & ~(size_t)7;
   L.Np = ((size_t)N + 7) & ~(size_t)7;
   size_t o = 0;
   L.off_ds = o;   o += align256((size_t)M * L.Np * 2);
-  L.off_dst = o;  o += tr ? align256((size_t)N * L.Mp * 2) : 0;
-  L.off_at = o;   o += tr ? align256((size_t)D * L.Mp * 2) : 0;
-  L.off_bt = o;   o += tr ? align256((size_t)D * L.Np * 2) : 0;
   L.off_part = o; o += align256((size_t)256 * kEpiWarps * 4);
   L.total = o + 256;
   return L;
 }
 size_t tc_bwd_ws(int M, int N, int D) { return bwd_layout(M, N, D).total; }
 
-__global__ void __launch_bounds__(256) transpose_pad_bf16_kernel(const __nv_bfloat16* __restrict__ in,
-                                                                 __nv_bfloat16* __restrict__ out, int rows, int cols,
-                                                                 int ld_out) {
-  // out[c][r] = in[r][c]; out rows padded to ld_out (pad columns zeroed)
-  __shared__ __nv_bfloat16 tile[32][34];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    const int r = r0 + ty + i, c = c0 + tx;
-    tile[ty + i][tx] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : __float2bfloat16_rn(0.f);
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 32; i += 8) {
-    const int c = c0 + ty + i, r = r0 + tx;
-    if (c < cols && r < ld_out) out[(size_t)c * ld_out + r] = tile[tx][ty + i];
-  }
-}
-
 int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
                 const float* row_lse, const float* col_lse, float w_row, float w_col, float w_diag,
                 const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
                 void* ws, size_t ws_bytes, int flags, cudaStream_t st) {
   const BwdLayout L = bwd_layout(M, N, D);
-  const bool tr = bwd_transposed_layout();
   XTAG_REQUIRE(ws && ws_bytes >= L.total, XTAG_ERR_WORKSPACE, "clip_bwd(tc): workspace %zu < %zu", ws_bytes, L.total);
   uint8_t* w = (uint8_t*)ws;
   __nv_bfloat16* dS = (__nv_bfloat16*)(w + L.off_ds);
-  __nv_bfloat16* dST = (__nv_bfloat16*)(w + L.off_dst);
-  __nv_bfloat16* At = (__nv_bfloat16*)(w + L.off_at);
-  __nv_bfloat16* Bt = (__nv_bfloat16*)(w + L.off_bt);
   float* part = (float*)(w + L.off_part);
-
   int rc = XTAG_OK;
   if (!(flags & XTAG_BWD_REUSE_DS)) {
     // padding columns of dS (N not a multiple of 8) enter the K sum of dA: keep them zero
     if (L.Np != (size_t)N) XTAG_CUDA(cudaMemsetAsync(dS, 0, (size_t)M * L.Np * 2, st));
-    if (tr && dB && L.Mp != (size_t)M) XTAG_CUDA(cudaMemsetAsync(dST, 0, (size_t)N * L.Mp * 2, st));
-
     EpiParams ep = {};
     ep.scale_p = scale;
     ep.label_offset = label_offset;
@@ -757,7 +707,6 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
     ep.w_row = w_row; ep.w_col = w_col; ep.w_diag = w_diag;
     ep.grad_out = grad_out;
     ep.dS = dS; ep.ldds = (int)L.Np;
-    ep.dST = (tr && dB) ? dST : nullptr; ep.lddst = (int)L.Mp;
     ep.dscale_part = part;
     const int grid = tc_grid_for(M, N);
     rc = launch_tc<EPI_DS, false, false>(A, D, Bm, D, M, N, D, ep, st);
@@ -770,31 +719,17 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
   EpiParams es = {};
   es.ldc = D; es.c_is_bf16 = (grad_dtype == XTAG_BF16); es.alpha = 1.f; es.alpha_p = scale;
   if (dA) {
+    // dA[i,d] = s * sum_j dS[i,j] Bm[j,d]: A operand dS is K-major (j contiguous); B operand (n=d, k=j) is the
+    // feature matrix itself, [K=j rows][N=d contiguous] = MN-major
     es.C = dA;
-    if (!tr) {
-      // dA[i,d] = s * sum_j dS[i,j] Bm[j,d]: A operand dS is K-major (j contiguous); B operand (n=d, k=j) is the
-      // feature matrix itself, [K=j rows][N=d contiguous] = MN-major
-      rc = launch_tc<EPI_STORE, false, true>(dS, (long)L.Np, Bm, (long)D, M, D, N, es, st);
-    } else {
-      dim3 g((D + 31) / 32, (N + 31) / 32);
-      transpose_pad_bf16_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)Bm, Bt, N, D, (int)L.Np);
-      XTAG_CHECK_LAUNCH();
-      rc = launch_tc<EPI_STORE, false, false>(dS, (long)L.Np, Bt, (long)L.Np, M, D, N, es, st);
-    }
+    rc = launch_tc<EPI_STORE, false, true>(dS, (long)L.Np, Bm, (long)D, M, D, N, es, st);
     if (rc) return rc;
   }
   if (dB) {
+    // dB[j,d] = s * sum_i dS[i,j] A[i,d]: A operand (m=j, k=i) is dS read as [K=i rows][M=j contiguous];
+    // B operand (n=d, k=i) is A read as [K=i rows][N=d contiguous]: both MN-major, nothing is transposed
     es.C = dB;
-    if (!tr) {
-      // dB[j,d] = s * sum_i dS[i,j] A[i,d]: A operand (m=j, k=i) is dS read as [K=i rows][M=j contiguous];
-      // B operand (n=d, k=i) is A read as [K=i rows][N=d contiguous]: both MN-major, nothing is transposed
-      rc = launch_tc<EPI_STORE, true, true>(dS, (long)L.Np, A, (long)D, N, D, M, es, st);
-    } else {
-      dim3 g((D + 31) / 32, (M + 31) / 32);
-      transpose_pad_bf16_kernel<<<g, 256, 0, st>>>((const __nv_bfloat16*)A, At, M, D, (int)L.Mp);
-      XTAG_CHECK_LAUNCH();
-      rc = launch_tc<EPI_STORE, false, false>(dST, (long)L.Mp, At, (long)L.Mp, N, D, M, es, st);
-    }
+    rc = launch_tc<EPI_STORE, true, true>(dS, (long)L.Np, A, (long)D, N, D, M, es, st);
     if (rc) return rc;
   }
   return XTAG_OK;
