@@ -53,6 +53,14 @@ uint64_t    xtag_launch_count(void);
 /* Diagnostics for bench.py's roofline: while enabled, every tcgen05 launch is bracketed by CUDA events on
  * its stream.  xtag_prof_read synchronises them and returns up to `cap` records: tag (0 = K1 forward,
  * 1 = K2 dS producer, 2 = plain GEMM), duration in ms, algorithmic FLOPs (2*M*N*K).  enable(0/1) clears. */
+/* Runtime tuning bits of the tcgen05 kernels (no reference counterpart; diagnostics / A-B measurements):
+ *   bits [0,8)  L2 prefetch distance of the TMA producer in 64-wide k-blocks (0 = off)
+ *   bit 8       dS tile stores carry an L2 evict_first policy      bit 9   operand loads carry evict_last
+ *   bit 10      force the two-exponential dS epilogue (default: one exponential per element when the block's
+ *               row/column log-sum-exps are within 2^60 of each other, exact two-exp path otherwise)
+ * Initial value: environment variable XTAG_TC_TUNE (0 if unset).  set returns the previous value. */
+int         xtag_set_tune(int bits);
+int         xtag_get_tune(void);
 int         xtag_prof_enable(int on);
 int         xtag_prof_read(int* tags_host, float* ms_host, double* flops_host, int cap);
 
@@ -86,6 +94,20 @@ int xtag_clip_fwd(const void* A, const void* Bm, int dtype, int M, int N, int D,
                   const float* scale /* device scalar: logit_scale.exp() */, int label_offset,
                   float* row_lse, float* col_lse, float* diag,
                   void* ws, size_t ws_bytes, int impl, void* stream);
+
+/* K1 with deferred reductions, for a forward that consumes its columns block by block (chunk-pipelined feature
+ * gather): each xtag_clip_fwd_block launches only the fused GEMM of one column block
+ * Bm_blk [N, D] and leaves log2-domain partials behind,
+ *     row_part [row_parts][M]            row_parts = 2*ceil(N/256)   (xtag_clip_fwd_block_parts)
+ *     col_part [col_parts][col_ld] + j0  col_parts = ceil(M/128), j0 = the block's first global column
+ * The caller stacks the row partials of all blocks in one [sum row_parts][M] buffer, lets all blocks share one
+ * [col_parts][col_ld = all columns] buffer, and finishes the step with two xtag_lse_reduce_log2 calls
+ * (out[j] = ln sum_p 2^parts[p*n + j]).  tcgen05 path only (bf16, D % 8 == 0). */
+int xtag_clip_fwd_block_parts(int M, int N, int* row_parts, int* col_parts);
+int xtag_clip_fwd_block(const void* A, const void* Bm_blk, int dtype, int M, int N, int D,
+                        const float* scale, int label_offset,
+                        float* row_part, float* col_part, int col_ld, float* diag, void* stream);
+int xtag_lse_reduce_log2(const float* parts, int P, int n, float* out, void* stream);
 
 /* out[j] = log sum_w exp(parts[w*N + j]): merges the per-rank partial column LSEs after the
  * all-gather (the one exchange step of the sharded loss). */

@@ -20,8 +20,9 @@ def _f64(t):
 class ModelKernels:
     name = "model"
 
-    def __init__(self):
+    def __init__(self, fwd_blocks: bool = True):
         self.calls = []
+        self.fwd_blocks = fwd_blocks       # False: exercise the per-block clip_fwd + lse_combine host path
 
     # K3
     def l2norm_fwd(self, x, out_dtype, eps, want_transposed=False):
@@ -53,6 +54,31 @@ class ModelKernels:
         if label_offset >= 0:                      # -1: no labels in this column block, diag untouched
             diag.copy_(S[torch.arange(M), torch.arange(M) + label_offset].float())
         return torch.logsumexp(S, 1).float(), col, diag
+
+    # K1 with deferred reductions: same contract, expressed with per-block natural-log LSEs
+    def supports_fwd_blocks(self, A):
+        return self.fwd_blocks
+
+    def clip_fwd_blocks_begin(self, A, block_cols, col_out=None):
+        M, N = A.shape[0], int(sum(block_cols))
+        return dict(M=M, N=N, rows=[], col=torch.full((N,), float("nan"), dtype=torch.float32),
+                    diag=torch.zeros(M, dtype=torch.float32), col_out=col_out, planned=list(block_cols), k=0)
+
+    def clip_fwd_block(self, st, A, Bm_blk, scale, label_offset, col_lo):
+        assert Bm_blk.shape[0] == st["planned"][st["k"]], "blocks must be launched in the planned order"
+        st["k"] += 1
+        row, col, _ = self.clip_fwd(A, Bm_blk, scale, label_offset, diag_out=st["diag"])
+        st["rows"].append(row)
+        st["col"][col_lo:col_lo + Bm_blk.shape[0]] = col
+
+    def clip_fwd_blocks_end(self, st):
+        assert st["k"] == len(st["planned"]) and not torch.isnan(st["col"]).any(), "a column block was never launched"
+        row = torch.logsumexp(torch.stack(st["rows"]).double(), 0).float()
+        col = st["col"]
+        if st["col_out"] is not None:
+            st["col_out"].copy_(col)
+            col = st["col_out"]
+        return row, col, st["diag"]
 
     def lse_combine(self, parts):
         return torch.logsumexp(_f64(parts), 0).float()

@@ -125,12 +125,13 @@ def _worker4(rank, world, port, q):
         Il = [I_all[r * b:(r + 1) * b] for r in range(world)]
         Tl = [T_all[r * b:(r + 1) * b] for r in range(world)]
         errs = []
-        for pipeline in (True, False):
+        # pipelined with deferred block reductions, pipelined with per-block reductions, not pipelined
+        for pipeline, fwd_blocks in ((True, True), (False, True), (True, False)):
             losses, dI, dT, ds = oracle.clip_loss_world(Il, Tl, scale, True, True)
             I = Il[rank].clone().requires_grad_(True)
             T = Tl[rank].clone().requires_grad_(True)
             s = torch.tensor(scale, dtype=torch.float64, requires_grad=True)
-            k = ModelKernels()
+            k = ModelKernels(fwd_blocks=fwd_blocks)
             mod = xt.ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world, pipeline=pipeline,
                               _kernels=k)
             loss = mod(I, T, s)
@@ -163,5 +164,6 @@ def test_cliploss_world4_pipelined_groups_of_two():
         fwd_pipe = errs[0][3]
         assert [c[2][0] for c in fwd_pipe] == [10, 10] and fwd_pipe[0][3] == (rank % 2) * 5 and fwd_pipe[1][3] == -1
         assert [c[2][0] for c in errs[1][3]] == [20]
+        assert errs[2][3] == fwd_pipe          # the two reduction strategies launch the same forward blocks
     for p in procs:
         p.join(timeout=60)

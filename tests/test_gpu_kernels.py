@@ -181,6 +181,99 @@ def test_clip_wide_dynamic_range(MK):
         assert rel_err(dA, dAm) < 2e-2 and rel_err(dB, dBm) < 2e-2
 
 
+@pytest.mark.parametrize("tune", [0x000, 0x400, 0x008, 0x004, 0x300, 0x30c])
+@pytest.mark.parametrize("M,N,D,off,scale", [(130, 300, 72, 100, 14.285714), (512, 1024, 512, 256, 100.0),
+                                             (1024, 1024, 1024, 0, 30.0)])
+def test_tc_tune_bits_parity(MK, tune, M, N, D, off, scale):
+    """Every runtime tuning bit of the tcgen05 kernels (xtag_set_tune: L2 prefetch distance, L2 cache hints, the
+    one-exp / two-exp dS epilogue) is a pure performance knob: forward and backward stay within the bf16 bars."""
+    from xtag_clip_b200.kernels import CudaKernels
+    K = CudaKernels(impl=2)
+    old = K.lib.xtag_set_tune(tune)
+    try:
+        assert K.lib.xtag_get_tune() == tune
+        I, T = feats(M + D + tune, max(M, N), D, corr=0.1, dtype=torch.bfloat16)
+        A = I[:M].contiguous()
+        Bm = torch.roll(T[:N], shifts=off, dims=0).contiguous() if off else T[:N].contiguous()
+        s = torch.tensor([scale])
+        row, col, diag = K.clip_fwd(A.cuda(), Bm.cuda(), s.cuda(), off)
+        rm, cm, dm = MK.clip_fwd(A, Bm, s, off)
+        assert rel_err(row, rm) < 2e-5 and rel_err(col, cm) < 2e-5 and rel_err(diag, dm) < 2e-5
+        g = torch.tensor(1.3)
+        w = (0.5 / M, 0.5 / M, 1.0 / M)
+        dA, dB, ds = K.clip_bwd(A.cuda(), Bm.cuda(), s.cuda(), off, rm.cuda(), cm.cuda(), *w, g.cuda(), True, True,
+                                torch.bfloat16)
+        dAm, dBm, dsm = MK.clip_bwd(A, Bm, s, off, rm, cm, *w, g, True, True, torch.float64)
+        assert rel_err(dA, dAm) < 2e-2 and rel_err(dB, dBm) < 2e-2
+        assert abs(float(ds) - float(dsm)) <= 1e-3 * abs(float(dsm)) + 2e-5
+        # weights with a zero column term and +inf column LSEs (local_loss without gather_with_grad)
+        never = torch.full((N,), float("inf"))
+        dA2, _, _ = K.clip_bwd(A.cuda(), Bm.cuda(), s.cuda(), off, rm.cuda(), never.cuda(), 0.5 / M, 0.0, 0.5 / M,
+                               g.cuda(), True, False, torch.bfloat16)
+        dA2m, _, _ = MK.clip_bwd(A, Bm, s, off, rm, never, 0.5 / M, 0.0, 0.5 / M, g, True, False, torch.float64)
+        assert torch.isfinite(dA2.float()).all() and rel_err(dA2, dA2m) < 2e-2
+        # a zero row term (column-softmax gradient only)
+        _, dB3, _ = K.clip_bwd(A.cuda(), Bm.cuda(), s.cuda(), off, rm.cuda(), cm.cuda(), 0.0, 0.5 / M, 0.5 / M,
+                               g.cuda(), False, True, torch.bfloat16)
+        _, dB3m, _ = MK.clip_bwd(A, Bm, s, off, rm, cm, 0.0, 0.5 / M, 0.5 / M, g, False, True, torch.float64)
+        assert torch.isfinite(dB3.float()).all() and rel_err(dB3, dB3m) < 2e-2
+    finally:
+        K.lib.xtag_set_tune(old)
+
+
+def test_ds_one_exp_matches_two_exp(MK):
+    """The one-exponential dS epilogue against the two-exponential one on the same inputs, including blocks whose
+    row / column log-sum-exps differ by more than the fast-path range (they must fall back, not overflow)."""
+    from xtag_clip_b200.kernels import CudaKernels
+    K = CudaKernels(impl=2)
+    I, T = feats(11, 768, 256, corr=0.0, dtype=torch.bfloat16)
+    T[:200] = I[:200]                      # S_ii = 100 for these rows: row LSE ~ 144 (log2) vs ~ 12 elsewhere
+    I[300:310] *= 3.0
+    s = torch.tensor([100.0])
+    rm, cm, dm = MK.clip_fwd(I, T, s, 0)
+    outs = []
+    for tune in (0x000, 0x400):
+        old = K.lib.xtag_set_tune(tune)
+        try:
+            outs.append(K.clip_bwd(I.cuda(), T.cuda(), s.cuda(), 0, rm.cuda(), cm.cuda(), 1 / 1536, 1 / 1536, 1 / 768,
+                                   torch.tensor(1.0).cuda(), True, True, torch.float32))
+        finally:
+            K.lib.xtag_set_tune(old)
+    dAm, dBm, _ = MK.clip_bwd(I, T, s, 0, rm, cm, 1 / 1536, 1 / 1536, 1 / 768, torch.tensor(1.0), True, True,
+                              torch.float64)
+    for dA, dB, ds in outs:
+        assert torch.isfinite(dA).all() and torch.isfinite(dB).all() and torch.isfinite(ds).all()
+        assert rel_err(dA, dAm) < 2e-2 and rel_err(dB, dBm) < 2e-2
+    assert rel_err(outs[0][0], outs[1][0]) < 5e-3 and rel_err(outs[0][1], outs[1][1]) < 5e-3
+
+
+@pytest.mark.parametrize("M,D,blocks,own", [(256, 512, [(256, 512), (0, 256), (512, 1024)], 1),
+                                            (130, 72, [(0, 130), (130, 300)], 0),
+                                            (1024, 1024, [(1024, 2048), (0, 1024), (2048, 4096)], 0)])
+def test_clip_fwd_blocks_deferred_reductions(K, MK, M, D, blocks, own):
+    """xtag_clip_fwd_block + xtag_lse_reduce_log2: the forward launched per column block (any order, labels in one
+    block only) with the row / column reductions done once equals the single-launch forward."""
+    N = max(hi for _, hi in blocks)
+    I, T = feats(M + D, max(M, N), D, corr=0.2, dtype=torch.bfloat16)
+    A = I[:M].contiguous()
+    lo_own = blocks[own][0]
+    off = lo_own                                             # labels (i, off + i) live in the `own` block
+    Bm = torch.roll(T[:N], shifts=off, dims=0).contiguous()
+    s = torch.tensor([20.0])
+    Ac, Bc, sc = A.cuda(), Bm.cuda(), s.cuda()
+    assert K.supports_fwd_blocks(Ac)
+    col_out = torch.empty(N, dtype=torch.float32, device="cuda")
+    st = K.clip_fwd_blocks_begin(Ac, [hi - lo for lo, hi in blocks], col_out=col_out)
+    for i, (lo, hi) in enumerate(blocks):
+        K.clip_fwd_block(st, Ac, Bc[lo:hi], sc, off - lo if i == own else -1, lo)
+    row, col, diag = K.clip_fwd_blocks_end(st)
+    assert col.data_ptr() == col_out.data_ptr()
+    rm, cm, dm = MK.clip_fwd(A, Bm, s, off)
+    assert rel_err(row, rm) < 2e-5 and rel_err(col, cm) < 2e-5 and rel_err(diag, dm) < 2e-5
+    r1, c1, d1 = K.clip_fwd(Ac, Bc, sc, off)
+    assert rel_err(row, r1) < 1e-6 and rel_err(col, c1) < 1e-6 and torch.equal(diag, d1)
+
+
 def test_lse_combine(K):
     parts = torch.randn(5, 1000) * 30
     parts[2, 10] = -float("inf")

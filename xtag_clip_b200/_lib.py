@@ -21,6 +21,8 @@ SIGNATURES = {
     "xtag_last_error": (c_char_p, []),
     "xtag_device_check": (c_int, []),
     "xtag_launch_count": (c_uint64, []),
+    "xtag_set_tune": (c_int, [c_int]),
+    "xtag_get_tune": (c_int, []),
     "xtag_prof_enable": (c_int, [c_int]),
     "xtag_prof_read": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "xtag_l2norm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
@@ -29,6 +31,10 @@ SIGNATURES = {
     "xtag_clip_fwd_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "xtag_clip_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "xtag_clip_fwd_block_parts": (c_int, [c_int, c_int, c_void_p, c_void_p]),
+    "xtag_clip_fwd_block": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                    c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "xtag_lse_reduce_log2": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "xtag_lse_combine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "xtag_lse_combine_ptrs": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "xtag_sum_ptrs_bf16": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),

@@ -19,6 +19,11 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
                 const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
                 void* ws, size_t ws_bytes, int flags, cudaStream_t st);
 
+void tc_fwd_block_parts(int M, int N, int* row_parts, int* col_parts);
+int tc_clip_fwd_block(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
+                      float* row_part, float* col_part, int col_ld, float* diag, cudaStream_t st);
+int launch_lse_reduce(const float* parts, int P, int n, float in_mul, float out_mul, float* out, cudaStream_t st);
+
 // tcgen05 path needs bf16 operands whose rows are 16-byte multiples (TMA global stride rule)
 static bool tc_eligible(int dtype, int D) { return dtype == XTAG_BF16 && D % 8 == 0; }
 
@@ -87,4 +92,31 @@ extern "C" int xtag_clip_bwd(const void* A, const void* Bm, int dtype, int M, in
                        grad_dtype, dscale, ws, ws_bytes, flags, (cudaStream_t)stream);
   return simt_clip_bwd(A, Bm, dtype, M, N, D, scale, label_offset, row_lse, col_lse, w_row, w_col, w_diag, grad_out,
                        dA, dB, grad_dtype, dscale, ws, ws_bytes, flags, (cudaStream_t)stream);
+}
+
+// ---- forward with deferred reductions (one launch per arriving column block, two reductions per step) -----------
+extern "C" int xtag_clip_fwd_block_parts(int M, int N, int* row_parts, int* col_parts) {
+  XTAG_REQUIRE(M > 0 && N > 0 && row_parts && col_parts, XTAG_ERR_INVALID, "clip_fwd_block_parts: bad arguments");
+  tc_fwd_block_parts(M, N, row_parts, col_parts);
+  return XTAG_OK;
+}
+
+extern "C" int xtag_clip_fwd_block(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale,
+                                   int label_offset, float* row_part, float* col_part, int col_ld, float* diag,
+                                   void* stream) {
+  XTAG_REQUIRE(A && Bm && scale && row_part && col_part && diag, XTAG_ERR_INVALID, "clip_fwd_block: null pointer");
+  XTAG_REQUIRE(M > 0 && N > 0 && D > 0 && col_ld >= N, XTAG_ERR_INVALID,
+               "clip_fwd_block: bad shape M=%d N=%d D=%d col_ld=%d", M, N, D, col_ld);
+  XTAG_REQUIRE(tc_eligible(dtype, D), XTAG_ERR_UNSUPPORTED,
+               "clip_fwd_block: tcgen05 path only (bf16 inputs, D %% 8 == 0); use xtag_clip_fwd per block otherwise");
+  XTAG_REQUIRE(label_offset == -1 || (label_offset >= 0 && (long)label_offset + M <= (long)N), XTAG_ERR_INVALID,
+               "clip_fwd_block: labels [%d, %d) fall outside the %d columns", label_offset, label_offset + M, N);
+  int rc = xtag_device_check();
+  if (rc) return rc;
+  return tc_clip_fwd_block(A, Bm, M, N, D, scale, label_offset, row_part, col_part, col_ld, diag, (cudaStream_t)stream);
+}
+
+extern "C" int xtag_lse_reduce_log2(const float* parts, int P, int n, float* out, void* stream) {
+  XTAG_REQUIRE(parts && out && P > 0 && n > 0, XTAG_ERR_INVALID, "lse_reduce_log2: bad arguments");
+  return launch_lse_reduce(parts, P, n, 1.f, kLn2, out, (cudaStream_t)stream);
 }

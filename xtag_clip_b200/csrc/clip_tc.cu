@@ -50,7 +50,8 @@ struct EpiParams {
   const float* scale_p;   // device scalar: logit scale (natural units)
   int label_offset;
   float* row_part;        // [2*num_n][M]   log2-domain LSE partial per (n tile, column half)
-  float* col_part;        // [num_m][N]     log2-domain LSE partial per m tile
+  float* col_part;        // [num_m][col_ld] log2-domain LSE partial per m tile (col_ld >= N: several column blocks
+  int col_ld;             //                 of one forward may share a buffer, each at its own column offset)
   float* diag;            // [M]            natural units
   // EPI_DS
   const float* row_lse;   // [M] natural
@@ -66,7 +67,13 @@ struct EpiParams {
   int c_is_bf16;
   float alpha;            // C = alpha * (alpha_p ? *alpha_p : 1) * acc
   const float* alpha_p;
+  // all epilogues: runtime tuning bits (xtag_set_tune): [0,8) L2 prefetch distance in k-blocks (0 = off),
+  // bit 8 dS tile stores carry an L2 evict_first hint, bit 9 operand loads carry an L2 evict_last hint,
+  // bit 10 forces the two-exponential dS path
+  int tune;
 };
+constexpr int kTunePrefetchMask = 0xff, kTuneStoreEvictFirst = 0x100, kTuneLoadEvictLast = 0x200,
+              kTuneDsTwoExp = 0x400;
 
 __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
   const int per_group = kGroupM * num_n;
@@ -243,17 +250,25 @@ __device__ __forceinline__ void lse_tile(const EpiParams& ep, uint32_t taddr, fl
     if (mx > -INFINITY)
       out = mx + fast_log2(fast_exp2(p0 - mx) + fast_exp2(p1 - mx) + fast_exp2(p2 - mx) + fast_exp2(p3 - mx));
     const int gj = n_base + c;
-    if (FULL || gj < N) ep.col_part[(size_t)m_blk * N + gj] = out;
+    if (FULL || gj < N) ep.col_part[(size_t)m_blk * ep.col_ld + gj] = out;
   }
 }
 
-// K2a: dS = g * ( 2^(a*sl2 - rl2') + 2^(a*sl2 - cl2'_j) ) - g*w_diag*[label], the (non-negative) weights folded
-// into the exponent offsets (one FFMA + one MUFU per term).  scratch[0..127] = per-column offsets cl2'.
+// K2a: dS = g * ( w_row * 2^(a*sl2 - rl2_i) + w_col * 2^(a*sl2 - cl2_j) ) - g*w_diag*[label]   (log2 domain).
+//   FAST  one exponential per element: with e_ij = 2^(a*sl2 - rl2_i),
+//           dS_ij = e_ij * ( g*w_row + (g*w_col*2^(rl2_i - nu)) * 2^(nu - cl2_j) )
+//         the bracket is one FFMA of a per-row and a per-column factor (nu = a reference common to the 128 columns
+//         of this half).  Exact up to rounding while |rl2_i - cl2_j| <= kDsFastRange for the whole 32 x 128 block
+//         (no factor over/underflows); the caller checks that per warp and otherwise takes
+//   !FAST the (non-negative) weights folded into two exponent offsets: one FFMA + one MUFU per term.
+// scratch[0..127] = per-column offsets cl2' (two-exp path), scratch[128..255] = per-column factors 2^(nu - cl2_j).
 // Returns this thread's partial of sum dS_ij * a_ij (= d logit_scale).
-template <bool FULL>
+constexpr float kDsFastRange = 60.f;
+template <bool FULL, bool FAST>
 __device__ __forceinline__ float ds_tile(const EpiParams& ep, const CUtensorMap* tmC, uint32_t taddr,
                                          const float* scratch, uint32_t ostage, int gi, int row_blk, int n_base,
-                                         float nrl2, int lane, int M, int N) {
+                                         float nrl2, float gwr, float gwc_r, uint64_t store_policy, int lane, int M,
+                                         int N) {
   const float sl2 = ep.scale_p[0] * kLog2e;
   const float g = ep.grad_out[0];
   const float gwd = g * ep.w_diag;
@@ -269,14 +284,20 @@ __device__ __forceinline__ float ds_tile(const EpiParams& ep, const CUtensorMap*
     float d[32];
 #pragma unroll
     for (int j4 = 0; j4 < 8; ++j4) {
-      const float4 c4 = *reinterpret_cast<const float4*>(scratch + ch * 32 + j4 * 4);
-      const float ncl2[4] = {-c4.x, -c4.y, -c4.z, -c4.w};
+      const float4 c4 = *reinterpret_cast<const float4*>(scratch + (FAST ? 128 : 0) + ch * 32 + j4 * 4);
+      const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int j = j4 * 4 + u;
         const float a = __uint_as_float(r[j]);
-        // out-of-range rows / columns carry offset -inf: their terms are exactly 0 (and are never stored)
-        d[j] = g * (fast_exp2(fmaf(a, sl2, nrl2)) + fast_exp2(fmaf(a, sl2, ncl2[u])));
+        if (FAST) {
+          // out-of-range rows carry nrl2 = -inf (e = 0, finite factors); out-of-range columns are never stored
+          // and multiply a zero accumulator in the d(logit_scale) sum
+          d[j] = fast_exp2(fmaf(a, sl2, nrl2)) * fmaf(gwc_r, cc[u], gwr);
+        } else {
+          // out-of-range rows / columns carry offset -inf: their terms are exactly 0 (and are never stored)
+          d[j] = g * (fast_exp2(fmaf(a, sl2, nrl2)) + fast_exp2(fmaf(a, sl2, -cc[u])));
+        }
       }
     }
     if (row_ok && lab >= c0 && lab < c0 + 32) {
@@ -303,7 +324,8 @@ __device__ __forceinline__ float ds_tile(const EpiParams& ep, const CUtensorMap*
       fence_proxy_async();                                  // generic-proxy writes -> visible to the TMA engine
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(tmC, ostage, c0, row_blk);
+        if (store_policy) tma_store_2d_hint(tmC, ostage, c0, row_blk, store_policy);
+        else              tma_store_2d(tmC, ostage, c0, row_blk);
         tma_store_commit();
       }
     }
@@ -416,28 +438,66 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const int pf_dist = ep.tune & kTunePrefetchMask;
+      const uint64_t ld_policy = (ep.tune & kTuneLoadEvictLast) ? l2_policy_evict_last() : 0;
+      // box (64 inner elements x rows) origin of operand X for block index blk and k-block kb
+      auto load_a = [&](uint32_t sa, uint32_t fb, int m_blk, int kb) {
+        if constexpr (A_MN) {
+#pragma unroll
+          for (int u = 0; u < BM / 64; ++u) {
+            if (ld_policy) tma_load_2d_hint(sa + u * (BK * 128), &tmA, fb, m_blk * BM + u * 64, kb * BK, ld_policy);
+            else           tma_load_2d(sa + u * (BK * 128), &tmA, fb, m_blk * BM + u * 64, kb * BK);
+          }
+        } else {
+          if (ld_policy) tma_load_2d_hint(sa, &tmA, fb, kb * BK, m_blk * BM, ld_policy);
+          else           tma_load_2d(sa, &tmA, fb, kb * BK, m_blk * BM);
+        }
+      };
+      auto load_b = [&](uint32_t sb, uint32_t fb, int n_blk, int kb) {
+        if constexpr (B_MN) {
+#pragma unroll
+          for (int u = 0; u < BN / 64; ++u) {
+            if (ld_policy) tma_load_2d_hint(sb + u * (BK * 128), &tmB, fb, n_blk * BN + u * 64, kb * BK, ld_policy);
+            else           tma_load_2d(sb + u * (BK * 128), &tmB, fb, n_blk * BN + u * 64, kb * BK);
+          }
+        } else {
+          if (ld_policy) tma_load_2d_hint(sb, &tmB, fb, kb * BK, n_blk * BN, ld_policy);
+          else           tma_load_2d(sb, &tmB, fb, kb * BK, n_blk * BN);
+        }
+      };
+      auto prefetch = [&](int m_blk, int n_blk, int kb) {
+        if constexpr (A_MN) {
+#pragma unroll
+          for (int u = 0; u < BM / 64; ++u) tma_prefetch_2d(&tmA, m_blk * BM + u * 64, kb * BK);
+        } else {
+          tma_prefetch_2d(&tmA, kb * BK, m_blk * BM);
+        }
+        if constexpr (B_MN) {
+#pragma unroll
+          for (int u = 0; u < BN / 64; ++u) tma_prefetch_2d(&tmB, n_blk * BN + u * 64, kb * BK);
+        } else {
+          tma_prefetch_2d(&tmB, kb * BK, n_blk * BN);
+        }
+      };
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
         tile_coords(tile, num_m, num_n, m_blk, n_blk);
+        int m_nxt = -1, n_nxt = -1;
+        if (pf_dist && tile + (int)gridDim.x < num_tiles) tile_coords(tile + gridDim.x, num_m, num_n, m_nxt, n_nxt);
         for (int kb = 0; kb < num_k; ++kb) {
+          if (pf_dist) {
+            // pull the operands pf_dist k-blocks ahead (possibly of this CTA's next tile) into L2 so the smem loads
+            // behind them see L2-hit latency: the 4-stage ring only covers ~1 us of lookahead
+            const int pk = kb + pf_dist;
+            if (pk < num_k) prefetch(m_blk, n_blk, pk);
+            else if (m_nxt >= 0 && pk - num_k < num_k) prefetch(m_nxt, n_nxt, pk - num_k);
+          }
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_arrive_expect_tx(fb, kStageBytes);
           const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
-          if constexpr (A_MN) {
-#pragma unroll
-            for (int u = 0; u < BM / 64; ++u)
-              tma_load_2d(sa + u * (BK * 128), &tmA, fb, m_blk * BM + u * 64, kb * BK);
-          } else {
-            tma_load_2d(sa, &tmA, fb, kb * BK, m_blk * BM);
-          }
-          if constexpr (B_MN) {
-#pragma unroll
-            for (int u = 0; u < BN / 64; ++u)
-              tma_load_2d(sa + kABytes + u * (BK * 128), &tmB, fb, n_blk * BN + u * 64, kb * BK);
-          } else {
-            tma_load_2d(sa + kABytes, &tmB, fb, kb * BK, n_blk * BN);
-          }
+          load_a(sa, fb, m_blk, kb);
+          load_b(sa + kABytes, fb, n_blk, kb);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -491,6 +551,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     float dscale_acc = 0.f;
+    [[maybe_unused]] const uint64_t store_policy = (ep.tune & kTuneStoreEvictFirst) ? l2_policy_evict_first() : 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_coords(tile, num_m, num_n, m_blk, n_blk);
@@ -509,23 +570,67 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (interior) lse_tile<true>(ep, taddr, scratch, gi, n_base, m_blk, n_blk, h, q, lane, M, N, tempty, bar_id);
         else          lse_tile<false>(ep, taddr, scratch, gi, n_base, m_blk, n_blk, h, q, lane, M, N, tempty, bar_id);
       } else if constexpr (EPI == EPI_DS) {
-        // stage the per-column exponent offsets of this half in smem before touching TMEM:
-        //   w_col * 2^(v - collse2) = 2^(v - (collse2 - log2 w_col)); w_col == 0 -> offset +inf -> term vanishes
+        // stage the per-column terms of this half in smem before touching TMEM:
+        //   [0,128)   two-exp path: exponent offsets, w_col * 2^(v - cl2) = 2^(v - (cl2 - log2 w_col));
+        //             w_col == 0 or a column past N -> offset +inf -> the term vanishes
+        //   [128,256) one-exp path: factors 2^(nu - cl2_j), nu = cl2 of the half's first column
+        //   [256,264) per-warp max / min of cl2 over the valid columns (range check of the one-exp path)
+        const bool has_col = ep.w_col > 0.f;
+        float nu = 0.f;
         {
           const int c = q * 32 + lane;
           const int gj = n_base + c;
-          const float lwc = (ep.w_col > 0.f) ? fast_log2(ep.w_col) : -INFINITY;
-          scratch[c] = (gj < N) ? ep.col_lse[gj] * kLog2e - lwc : INFINITY;
+          const bool cvalid = gj < N;
+          const float lwc = has_col ? fast_log2(ep.w_col) : -INFINITY;
+          const float cl2 = cvalid ? ep.col_lse[gj] * kLog2e : INFINITY;
+          if (has_col) nu = ep.col_lse[min(n_base, N - 1)] * kLog2e;
+          scratch[c] = cl2 - lwc;
+          scratch[128 + c] = (cvalid && has_col) ? fast_exp2(nu - cl2) : 0.f;
+          const float cmx = warp_max(cvalid ? cl2 : -INFINITY);
+          const float cmn = -warp_max(cvalid ? -cl2 : -INFINITY);
+          if (lane == 0) {
+            scratch[256 + q] = cmx;
+            scratch[260 + q] = cmn;
+          }
         }
-        const float lwr = (ep.w_row > 0.f) ? fast_log2(ep.w_row) : -INFINITY;
-        const float nrl2 = (gi < M) ? -(ep.row_lse[gi] * kLog2e - lwr) : -INFINITY;      // -(rl2 - log2 w_row)
+        const float g = ep.grad_out[0];
+        const float rl2 = (gi < M) ? ep.row_lse[gi] * kLog2e : INFINITY;
+        const float rmx = warp_max((gi < M) ? rl2 : -INFINITY);
+        const float rmn = -warp_max((gi < M) ? -rl2 : -INFINITY);
         named_bar_sync(bar_id, 128);
+        bool fast = (ep.tune & kTuneDsTwoExp) == 0;
+        if (fast && has_col) {
+          const float4 mx4 = *reinterpret_cast<const float4*>(scratch + 256);
+          const float4 mn4 = *reinterpret_cast<const float4*>(scratch + 260);
+          const float cmx = fmaxf(fmaxf(mx4.x, mx4.y), fmaxf(mx4.z, mx4.w));
+          const float cmn = fminf(fminf(mn4.x, mn4.y), fminf(mn4.z, mn4.w));
+          // every |rl2_i - cl2_j| of this warp's 32 x 128 block within range (NaN from inf - inf -> two-exp path)
+          fast = (rmx - cmn <= kDsFastRange) && (cmx - rmn <= kDsFastRange);
+        }
         mbar_wait(tfull, acc_phase);
         tc_fence_after();
         const uint32_t ostage = smem_u32(out_stage + e * 2048);
         const int row_blk = m_blk * BM + q * 32;
-        if (interior) dscale_acc += ds_tile<true>(ep, &tmC, taddr, scratch, ostage, gi, row_blk, n_base, nrl2, lane, M, N);
-        else          dscale_acc += ds_tile<false>(ep, &tmC, taddr, scratch, ostage, gi, row_blk, n_base, nrl2, lane, M, N);
+        if (fast) {
+          const float nrl2 = -rl2;                                                 // OOB row: -inf -> e = 0
+          const float gwr = g * ep.w_row;
+          const float gwc_r = (has_col && gi < M) ? g * ep.w_col * fast_exp2(rl2 - nu) : 0.f;
+          if (interior)
+            dscale_acc += ds_tile<true, true>(ep, &tmC, taddr, scratch, ostage, gi, row_blk, n_base, nrl2, gwr, gwc_r,
+                                              store_policy, lane, M, N);
+          else
+            dscale_acc += ds_tile<false, true>(ep, &tmC, taddr, scratch, ostage, gi, row_blk, n_base, nrl2, gwr, gwc_r,
+                                               store_policy, lane, M, N);
+        } else {
+          const float lwr = (ep.w_row > 0.f) ? fast_log2(ep.w_row) : -INFINITY;
+          const float nrl2 = (gi < M) ? -(rl2 - lwr) : -INFINITY;                  // -(rl2 - log2 w_row)
+          if (interior)
+            dscale_acc += ds_tile<true, false>(ep, &tmC, taddr, scratch, ostage, gi, row_blk, n_base, nrl2, 0.f, 0.f,
+                                               store_policy, lane, M, N);
+          else
+            dscale_acc += ds_tile<false, false>(ep, &tmC, taddr, scratch, ostage, gi, row_blk, n_base, nrl2, 0.f, 0.f,
+                                                store_policy, lane, M, N);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty);
@@ -606,8 +711,10 @@ static int make_store_tmap_bf16(CUtensorMap* tm, void* base, int rows, int cols,
 }
 
 template <int EPI, bool A_MN, bool B_MN>
-static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiParams& ep,
+static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiParams& ep_in,
                      cudaStream_t st) {
+  EpiParams ep = ep_in;
+  ep.tune = tc_tune();
   CUtensorMap tmA, tmB, tmC;
   memset(&tmC, 0, sizeof(tmC));
   if (EPI == EPI_DS) {
@@ -661,12 +768,32 @@ int tc_clip_fwd(const void* A, const void* Bm, int M, int N, int D, const float*
   ep.label_offset = label_offset;
   ep.row_part = (float*)ws;
   ep.col_part = (float*)((uint8_t*)ws + align256(2 * (size_t)num_n * M * 4));
+  ep.col_ld = N;
   ep.diag = diag;
   int rc = launch_tc<EPI_LSE, false, false>(A, D, Bm, D, M, N, D, ep, st);
   if (rc) return rc;
   rc = launch_lse_reduce(ep.row_part, 2 * num_n, M, 1.f, kLn2, row_lse, st);
   if (rc) return rc;
   return launch_lse_reduce(ep.col_part, num_m, N, 1.f, kLn2, col_lse, st);
+}
+
+// One column block of a forward whose reductions are deferred (chunk-pipelined multi-GPU gather): the kernel only
+// writes its log2-domain partials -- row_part [2*ceil(N/256)][M] (this block's slice of the caller's row-partial
+// buffer), col_part [ceil(M/128)][col_ld] at the block's column offset -- and the caller reduces all blocks at once.
+void tc_fwd_block_parts(int M, int N, int* row_parts, int* col_parts) {
+  *row_parts = 2 * ((N + BN - 1) / BN);
+  *col_parts = (M + BM - 1) / BM;
+}
+int tc_clip_fwd_block(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
+                      float* row_part, float* col_part, int col_ld, float* diag, cudaStream_t st) {
+  EpiParams ep = {};
+  ep.scale_p = scale;
+  ep.label_offset = label_offset;
+  ep.row_part = row_part;
+  ep.col_part = col_part;
+  ep.col_ld = col_ld;
+  ep.diag = diag;
+  return launch_tc<EPI_LSE, false, false>(A, D, Bm, D, M, N, D, ep, st);
 }
 
 // Backward workspace: dS [M][Np] bf16 (Np = N padded to 8 so rows stay 16-byte multiples) + d(logit_scale) partials.

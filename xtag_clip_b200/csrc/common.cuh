@@ -46,6 +46,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
   } while (0)
 
 int num_sms();
+int tc_tune();   // runtime tuning bits of the tcgen05 kernels (xtag_set_tune / XTAG_TC_TUNE)
 
 // opt-in per-launch timing (CUDA events on the launching stream), see xtag_prof_enable in the header
 struct ProfScope {

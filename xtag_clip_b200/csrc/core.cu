@@ -1,5 +1,6 @@
 // Library plumbing: version, thread-local error string, device check, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -30,6 +31,20 @@ int num_sms() {
       return 148;
   }
   return cached;
+}
+
+// runtime tuning bits of the tcgen05 kernels (see EpiParams::tune in clip_tc.cu); initialised once from the
+// environment variable XTAG_TC_TUNE, overridable with xtag_set_tune()
+static std::atomic<int> g_tune{-1};
+static constexpr int kDefaultTune = 0;
+int tc_tune() {
+  int t = g_tune.load(std::memory_order_relaxed);
+  if (t < 0) {
+    const char* e = getenv("XTAG_TC_TUNE");
+    t = e ? (int)strtol(e, nullptr, 0) & 0xffff : kDefaultTune;
+    g_tune.store(t, std::memory_order_relaxed);
+  }
+  return t;
 }
 
 struct ProfRec {
@@ -89,6 +104,14 @@ int xtag_prof_read(int* tags, float* ms, double* work, int cap) {
   return n;
 }
 
+
+int xtag_set_tune(int bits) {
+  const int old = xtag::tc_tune();
+  xtag::g_tune.store(bits & 0xffff, std::memory_order_relaxed);
+  return old;
+}
+
+int xtag_get_tune(void) { return xtag::tc_tune(); }
 
 int xtag_version(void) { return XTAG_ABI_VERSION; }
 

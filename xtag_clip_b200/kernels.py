@@ -97,6 +97,58 @@ class CudaKernels:
               "xtag_clip_fwd")
         return row_lse, col_lse, diag
 
+    # ---- K1, deferred reductions (one GEMM launch per column block, two reductions per step) ---------------
+    def supports_fwd_blocks(self, A: torch.Tensor) -> bool:
+        return A.is_cuda and A.dtype == torch.bfloat16 and A.shape[1] % 8 == 0 and self.impl in (IMPL_AUTO, _lib.IMPL_TC)
+
+    def clip_fwd_blocks_begin(self, A: torch.Tensor, block_cols, col_out: Optional[torch.Tensor] = None):
+        """Plan a forward over column blocks of `block_cols` columns each (in launch order; their position inside
+        the [sum(block_cols)] column range is given per launch).  Returns the state `clip_fwd_block` /
+        `clip_fwd_blocks_end` take."""
+        _cuda(A)
+        M = A.shape[0]
+        import ctypes
+        rp, cp = ctypes.c_int(0), ctypes.c_int(0)
+        offs, tot = [], 0
+        for n in block_cols:
+            check(self.lib.xtag_clip_fwd_block_parts(M, int(n), ctypes.byref(rp), ctypes.byref(cp)),
+                  "xtag_clip_fwd_block_parts")
+            offs.append(tot)
+            tot += rp.value
+        Ncols = int(sum(block_cols))
+        dev = A.device
+        return dict(M=M, N=Ncols, row_off=offs, P=tot, num_m=cp.value,
+                    row_part=torch.empty((tot, M), dtype=torch.float32, device=dev),
+                    col_part=torch.empty((cp.value, Ncols), dtype=torch.float32, device=dev),
+                    diag=torch.empty(M, dtype=torch.float32, device=dev), col_out=col_out, k=0)
+
+    def clip_fwd_block(self, st, A: torch.Tensor, Bm_blk: torch.Tensor, scale: torch.Tensor, label_offset: int,
+                       col_lo: int):
+        """Launch K1 for the next planned block: Bm_blk holds global columns [col_lo, col_lo + rows(Bm_blk))."""
+        _cuda(A, Bm_blk, scale)
+        A, Bm_blk = A.contiguous(), Bm_blk.contiguous()
+        M, D = A.shape
+        n = Bm_blk.shape[0]
+        k = st["k"]
+        st["k"] = k + 1
+        row_part = st["row_part"][st["row_off"][k]:]
+        col_part = st["col_part"][:, col_lo:]
+        check(self.lib.xtag_clip_fwd_block(_p(A), _p(Bm_blk), _dt(A), M, n, D, _p(scale), int(label_offset),
+                                           row_part.data_ptr(), col_part.data_ptr(), st["N"], _p(st["diag"]),
+                                           _stream()), "xtag_clip_fwd_block")
+
+    def clip_fwd_blocks_end(self, st):
+        """-> (row_lse [M], col_lse_partial [N] (written into col_out when given), diag [M])"""
+        dev = st["row_part"].device
+        row_lse = torch.empty(st["M"], dtype=torch.float32, device=dev)
+        col = st["col_out"] if st["col_out"] is not None else torch.empty(st["N"], dtype=torch.float32, device=dev)
+        assert col.is_contiguous() and col.numel() == st["N"]
+        check(self.lib.xtag_lse_reduce_log2(_p(st["row_part"]), st["P"], st["M"], _p(row_lse), _stream()),
+              "xtag_lse_reduce_log2")
+        check(self.lib.xtag_lse_reduce_log2(_p(st["col_part"]), st["num_m"], st["N"], _p(col), _stream()),
+              "xtag_lse_reduce_log2")
+        return row_lse, col, st["diag"]
+
     def lse_combine(self, parts: torch.Tensor) -> torch.Tensor:
         _cuda(parts)
         parts = parts.contiguous()

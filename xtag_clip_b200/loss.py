@@ -193,16 +193,27 @@ class _FusedClipLoss(torch.autograd.Function):
             else:
                 plan = cfg.comm.pipelined_gather(txt, txt_all)    # batched NCCL P2P rounds
                 col_part = torch.empty(B, dtype=torch.float32, device=txt.device)
-            diag = torch.empty(b, dtype=torch.float32, device=txt.device)
-            row_parts = []
+            blocks = hasattr(K, "supports_fwd_blocks") and K.supports_fwd_blocks(img)
+            if blocks:
+                # one K1 launch per arriving block, the row / column reductions of all blocks once at the end
+                st = K.clip_fwd_blocks_begin(img, [hi - lo for lo, hi, _ in plan], col_out=col_part)
+            else:
+                diag = torch.empty(b, dtype=torch.float32, device=txt.device)
+                row_parts = []
             for lo, hi, ev in plan:
                 for e in (ev if isinstance(ev, (list, tuple)) else [ev]):
                     if e is not None:
                         torch.cuda.current_stream().wait_event(e)
                 lab = off - lo if lo <= off < hi else -1          # only the rank's own block holds its labels
-                rp, _, _ = K.clip_fwd(img, txt_all[lo:hi], scale, lab, col_out=col_part[lo:hi], diag_out=diag)
-                row_parts.append(rp)
-            row_lse = K.lse_combine(torch.stack(row_parts)) if len(row_parts) > 1 else row_parts[0]
+                if blocks:
+                    K.clip_fwd_block(st, img, txt_all[lo:hi], scale, lab, lo)
+                else:
+                    rp, _, _ = K.clip_fwd(img, txt_all[lo:hi], scale, lab, col_out=col_part[lo:hi], diag_out=diag)
+                    row_parts.append(rp)
+            if blocks:
+                row_lse, _, diag = K.clip_fwd_blocks_end(st)
+            else:
+                row_lse = K.lse_combine(torch.stack(row_parts)) if len(row_parts) > 1 else row_parts[0]
             if sx is not None:
                 sx.end_gather()
                 col_lse = sx.combine_cols(K)                      # barrier + one kernel over the W peer buffers
