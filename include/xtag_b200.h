@@ -58,6 +58,8 @@ uint64_t    xtag_launch_count(void);
  *   bit 8       dS tile stores carry an L2 evict_first policy      bit 9   operand loads carry evict_last
  *   bit 10      force the two-exponential dS epilogue (default: one exponential per element when the block's
  *               row/column log-sum-exps are within 2^60 of each other, exact two-exp path otherwise)
+ *   bit 11      K4 backward as ONE single-pass kernel (K and V streamed once, dK/dV by TMA tile stores) instead of
+ *               the query-major dQ kernel + key-major dK/dV kernel pair
  * Initial value: environment variable XTAG_TC_TUNE (0 if unset).  set returns the previous value. */
 int         xtag_set_tune(int bits);
 int         xtag_get_tune(void);

@@ -286,7 +286,17 @@ def test_lse_combine(K):
 @pytest.mark.parametrize("b,Lq,Lk,heads,dh", [(3, 44, 50, 4, 192), (2, 44, 197, 4, 192), (2, 44, 257, 4, 192),
                                               (2, 7, 5, 2, 16), (1, 44, 64, 4, 192), (2, 16, 33, 2, 64),
                                               (2, 30, 100, 3, 128), (1, 64, 130, 2, 256), (2, 1, 1, 4, 192)])
-def test_xattn(K, MK, dtype, b, Lq, Lk, heads, dh):
+@pytest.mark.parametrize("tune", [0x000, 0x800])
+def test_xattn(K, MK, dtype, b, Lq, Lk, heads, dh, tune):
+    """tune 0x800: the single-pass backward kernel (bf16 inputs; other dtypes / shapes ignore the bit)."""
+    old = K.lib.xtag_set_tune(tune)
+    try:
+        _xattn_case(K, MK, dtype, b, Lq, Lk, heads, dh)
+    finally:
+        K.lib.xtag_set_tune(old)
+
+
+def _xattn_case(K, MK, dtype, b, Lq, Lk, heads, dh):
     g = torch.Generator().manual_seed(b * 100 + Lk)
     H = heads * dh
     q = (torch.randn(b, Lq, H, generator=g) * 1.5).to(dtype)
@@ -307,6 +317,32 @@ def test_xattn(K, MK, dtype, b, Lq, Lk, heads, dh):
         return float((a64 - b64).abs().max()) <= 2 * tol * float(b64.abs().max()) + 1e-5
 
     assert close(dq, dqm) and close(dk, dkm) and close(dv, dvm)
+
+
+@pytest.mark.parametrize("b,Lq,Lk,heads,dh", [(64, 44, 197, 4, 192), (8, 44, 257, 4, 192), (5, 44, 50, 4, 192),
+                                              (3, 64, 300, 2, 128), (4, 20, 77, 8, 64)])
+def test_xattn_bwd_single_pass_matches_two_kernel(K, b, Lq, Lk, heads, dh):
+    """The single-pass backward against the two-kernel backward on the same inputs, with and without dropout (the
+    Philox mask is keyed by element index, so both must drop the same probabilities)."""
+    g = torch.Generator().manual_seed(Lk)
+    H = heads * dh
+    q = torch.randn(b, Lq, H, generator=g).bfloat16().cuda()
+    kv = torch.randn(b, Lk, 2 * H, generator=g).bfloat16().cuda()
+    k, v = kv[..., :H], kv[..., H:]
+    do = torch.randn(b, Lq, H, generator=g).bfloat16().cuda()
+    sc = 1 / math.sqrt(dh)
+    for p in (0.0, 0.1):
+        o, lse = K.xattn_fwd(q, k, v, heads, sc, p, 77, 5)
+        res = []
+        for tune in (0x000, 0x800):
+            old = K.lib.xtag_set_tune(tune)
+            try:
+                res.append(K.xattn_bwd(q, k, v, o, do, lse, heads, sc, p, 77, 5))
+            finally:
+                K.lib.xtag_set_tune(old)
+        for a, c in zip(*res):
+            assert torch.isfinite(a.float()).all() and torch.isfinite(c.float()).all()
+            assert rel_err(c, a) < 1.5e-2
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

@@ -53,6 +53,7 @@ __device__ __forceinline__ uint32_t swz(int row, int col) {
 }
 
 constexpr int XA_KT = 32;        // keys per pipeline stage
+constexpr int kTuneXattnFusedBwd = 0x800;   // xtag_set_tune bit 11: single-pass K4 backward
 constexpr int XA_MAXW = 4;       // up to 64 query rows
 
 // NCH = dh / 64
@@ -636,6 +637,340 @@ xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+// =============================================================================================================
+// Backward, single pass (default).  One CTA per (sample, head), NW = ceil(Lq / 16) warps, K and V streamed ONCE:
+// per 32-key tile
+//   S = Q K^T, dP = dO V^T                         16 query rows per warp (as the forward)
+//   P = 2^(S*sl2 - lse2), Pd = P*mask, dS = P (dP*mask - delta) * scale
+//   dQ += dS K                                      A operand straight from the accumulator registers
+//   Pd, dS -> shared memory (bf16, [query][key])    so that every warp sees all Lq queries of the tile
+//   dV_tile = Pd^T dO, dK_tile = dS^T Q             contraction over the queries; the head dimension is split across
+//                                                   the warps (A = ldmatrix.trans of the staged Pd / dS)
+//   dV_tile / dK_tile -> swizzled staging tile -> TMA tile store (full 128-byte rows, rows past Lk clipped)
+// HBM traffic is the algorithmic minimum: q, k, v, o, dO read once, dq, dk, dv written once.
+// =============================================================================================================
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// byte offset of (row, 16-byte unit) in a [rows][32 keys] bf16 staging tile (64-byte rows, XOR swizzle so that
+// both the fragment stores and the transposed ldmatrix reads are bank-conflict free)
+__device__ __forceinline__ uint32_t swz64(int row, int unit) {
+  return (uint32_t)(row * 64 + ((unit ^ ((row >> 1) & 3)) << 4));
+}
+
+template <int NCH, int NW>
+__global__ void __launch_bounds__(32 * NW)
+xattn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                       const __grid_constant__ CUtensorMap tmDK, const __grid_constant__ CUtensorMap tmDV,
+                       const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                       const float* __restrict__ lse, __nv_bfloat16* __restrict__ dq,
+                       int Lq, int Lk, int heads, float sl2, float sm_scale, float p_drop, uint64_t seed,
+                       uint64_t offset) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int QROWS = 16 * NW;
+  constexpr uint32_t q_bytes = (uint32_t)NCH * QROWS * 128;
+  constexpr uint32_t q_pad = (q_bytes + 1023) & ~1023u;
+  constexpr uint32_t kv_chunk = XA_KT * 128;
+  constexpr uint32_t stage_bytes = 2 * NCH * kv_chunk;
+  constexpr int NPAIR = NCH * 4;                       // 16-column pairs of n8 tiles across the head dimension
+  constexpr int NP = (NPAIR + NW - 1) / NW;            // pairs owned by one warp in the dV / dK products
+  uint8_t* Qs = smem;
+  uint8_t* dOs = smem + q_pad;
+  uint8_t* KVs = smem + 2 * q_pad;
+  uint8_t* Os = KVs + 2 * stage_bytes;                 // [NCH][32][64] bf16 output staging (TMA 128B swizzle)
+  uint8_t* Ps = Os + NCH * kv_chunk;                   // [QROWS][32] bf16 dropped probabilities
+  uint8_t* dSs = Ps + QROWS * 64;                      // [QROWS][32] bf16 dS
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dSs + QROWS * 64);
+  float* delta_s = reinterpret_cast<float*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  constexpr int dh = NCH * 64;
+  const int HD = heads * dh;
+  const int num_tiles = (Lk + XA_KT - 1) / XA_KT;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmDO);
+    prefetch_tmap(&tmDK); prefetch_tmap(&tmDV);
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue_tile = [&](int t) {
+    const int st = t & 1;
+    const uint32_t fb = smem_u32(&bars[1 + st]);
+    const uint32_t base = smem_u32(KVs + st * stage_bytes);
+    mbar_arrive_expect_tx(fb, stage_bytes);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      tma_load_3d(base + c * kv_chunk, &tmK, fb, h * dh + c * 64, t * XA_KT, b);
+      tma_load_3d(base + (NCH + c) * kv_chunk, &tmV, fb, h * dh + c * 64, t * XA_KT, b);
+    }
+  };
+  if (tid == 0) {
+    const uint32_t qb = smem_u32(&bars[0]);
+    mbar_arrive_expect_tx(qb, 2 * q_bytes);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      tma_load_3d(smem_u32(Qs) + c * QROWS * 128, &tmQ, qb, h * dh + c * 64, 0, b);
+      tma_load_3d(smem_u32(dOs) + c * QROWS * 128, &tmDO, qb, h * dh + c * 64, 0, b);
+    }
+    issue_tile(0);
+  }
+  // delta_r = sum_c dO[r,c] * O[r,c] for this warp's 16 rows (O is only needed here: straight from global memory)
+  for (int rr = 0; rr < 16; ++rr) {
+    const int row = warp * 16 + rr;
+    float sacc = 0.f;
+    if (row < Lq) {
+      const __nv_bfloat16* op = o + ((size_t)b * Lq + row) * HD + h * dh;
+      const __nv_bfloat16* dp = d_o + ((size_t)b * Lq + row) * HD + h * dh;
+      for (int c = lane * 2; c < dh; c += 64) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(op + c));
+        const float2 d2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp + c));
+        sacc = fmaf(a.x, d2.x, fmaf(a.y, d2.y, sacc));
+      }
+    }
+    sacc = warp_sum(sacc);
+    if (lane == 0) delta_s[row] = sacc;
+  }
+  __syncwarp();
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const int row0 = warp * 16 + g;
+  float lse2[2], dl[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = row0 + r * 8;
+    lse2[r] = (row < Lq) ? lse[(size_t)bh * Lq + row] * kLog2e : INFINITY;    // padded query rows: P = 0
+    dl[r] = delta_s[row];
+  }
+  float qacc[NCH * 8][4];
+#pragma unroll
+  for (int i = 0; i < NCH * 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) qacc[i][j] = 0.f;
+
+  mbar_wait(smem_u32(&bars[0]), 0);
+  const uint32_t q_base = smem_u32(Qs), do_base = smem_u32(dOs);
+  const uint32_t ps_base = smem_u32(Ps), ds_base = smem_u32(dSs), os_base = smem_u32(Os);
+  const int qrow = warp * 16 + (lane & 15);
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+
+  for (int t = 0; t < num_tiles; ++t) {
+    const int st = t & 1;
+    if (tid == 0 && t + 1 < num_tiles) issue_tile(t + 1);      // stage st^1 was released by the last barrier of t-1
+    mbar_wait(smem_u32(&bars[1 + st]), (uint32_t)((t >> 1) & 1));
+    const uint32_t k_base = smem_u32(KVs + st * stage_bytes);
+    const uint32_t v_base = k_base + NCH * kv_chunk;
+    const int key0 = t * XA_KT;
+    // ---- S = Q K^T and dP = dO V^T for this warp's 16 query rows ----
+    float sacc[XA_KT / 8][4], pacc[XA_KT / 8][4];
+#pragma unroll
+    for (int i = 0; i < XA_KT / 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sacc[i][j] = 0.f; pacc[i][j] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < NCH * 4; ++kk) {
+      const int c = kk >> 2, kx = (kk & 3) * 16;
+      uint32_t aq[4], ad[4];
+      ldsm_x4(q_base + c * QROWS * 128 + swz(qrow, kx + ((lane >> 4) << 3)), aq);
+      ldsm_x4(do_base + c * QROWS * 128 + swz(qrow, kx + ((lane >> 4) << 3)), ad);
+#pragma unroll
+      for (int np = 0; np < XA_KT / 16; ++np) {
+        const int krow = np * 16 + ((lane >> 4) << 3) + (lane & 7);
+        const int kcol = kx + (((lane >> 3) & 1) << 3);
+        uint32_t bk[4], bv[4];
+        ldsm_x4(k_base + c * kv_chunk + swz(krow, kcol), bk);
+        ldsm_x4(v_base + c * kv_chunk + swz(krow, kcol), bv);
+        mma_bf16(sacc[2 * np], aq, bk[0], bk[1]);
+        mma_bf16(sacc[2 * np + 1], aq, bk[2], bk[3]);
+        mma_bf16(pacc[2 * np], ad, bv[0], bv[1]);
+        mma_bf16(pacc[2 * np + 1], ad, bv[2], bv[3]);
+      }
+    }
+    // ---- elementwise: sacc <- dS, pacc <- dropped probabilities ----
+#pragma unroll
+    for (int i = 0; i < XA_KT / 8; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int key = key0 + i * 8 + t4 * 2 + (j & 1);
+        const int r = j >> 1;
+        const float p = (key < Lk) ? fast_exp2(fmaf(sacc[i][j], sl2, -lse2[r])) : 0.f;
+        float m = 1.f;
+        if (p_drop > 0.f) {
+          const uint64_t idx = ((uint64_t)bh * Lq + (row0 + r * 8)) * Lk + key;
+          m = philox_keep(seed, offset, idx, p_drop) ? keep_scale : 0.f;
+        }
+        sacc[i][j] = p * (pacc[i][j] * m - dl[r]) * sm_scale;    // dS (w.r.t. q.k before the 1/sqrt(dh) scale)
+        pacc[i][j] = p * m;
+      }
+    }
+    // ---- stage Pd and dS ([query][key], bf16) for the key-major products ----
+#pragma unroll
+    for (int i = 0; i < XA_KT / 8; ++i) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = row0 + r * 8;
+        const uint32_t off = swz64(row, i) + (uint32_t)(t4 * 4);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(ps_base + off), "r"(pack_bf16(pacc[i][2 * r], pacc[i][2 * r + 1]))
+                     : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(ds_base + off), "r"(pack_bf16(sacc[i][2 * r], sacc[i][2 * r + 1]))
+                     : "memory");
+      }
+    }
+    // ---- dQ += dS K (A operand from the accumulator registers) ----
+#pragma unroll
+    for (int ks = 0; ks < XA_KT / 16; ++ks) {
+      uint32_t a[4];
+      a[0] = pack_bf16(sacc[2 * ks][0], sacc[2 * ks][1]);
+      a[1] = pack_bf16(sacc[2 * ks][2], sacc[2 * ks][3]);
+      a[2] = pack_bf16(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
+      a[3] = pack_bf16(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
+#pragma unroll
+      for (int dn = 0; dn < NCH * 4; ++dn) {
+        const int krow = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+        const int kcol = dn * 16 + ((lane >> 4) << 3);
+        uint32_t bb[4];
+        ldsm_x4_t(k_base + (kcol >> 6) * kv_chunk + swz(krow, kcol & 63), bb);
+        mma_bf16(qacc[2 * dn], a, bb[0], bb[1]);
+        mma_bf16(qacc[2 * dn + 1], a, bb[2], bb[3]);
+      }
+    }
+    // the previous tile's dK store must have drained the staging tile before it is overwritten below
+    if (tid == 0) tma_store_wait_read();
+    __syncthreads();                                             // (E) Pd / dS of all warps staged; Os free
+
+    // ---- key-major products: pass 0 dV_tile = Pd^T dO, pass 1 dK_tile = dS^T Q ----
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const uint32_t a_base = pass == 0 ? ps_base : ds_base;
+      const uint32_t b_base = pass == 0 ? do_base : q_base;
+      float acc[2][2 * NP][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int i = 0; i < 2 * NP; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[mt][i][j] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < NW; ++ks) {
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          // A[key][query] = staged[query][key]: four transposed 8x8 blocks (keys 0-7 | 8-15) x (queries 0-7 | 8-15)
+          const int mat = lane >> 3;
+          const int qr = ks * 16 + ((mat >> 1) << 3) + (lane & 7);
+          ldsm_x4_t(a_base + swz64(qr, mt * 2 + (mat & 1)), a[mt]);
+        }
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) {
+          const int dn = warp * NP + pl;
+          if (dn < NPAIR) {
+            const int qr = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+            const int dc = dn * 16 + ((lane >> 4) << 3);
+            uint32_t bb[4];
+            ldsm_x4_t(b_base + (dc >> 6) * QROWS * 128 + swz(qr, dc & 63), bb);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              mma_bf16(acc[mt][2 * pl], a[mt], bb[0], bb[1]);
+              mma_bf16(acc[mt][2 * pl + 1], a[mt], bb[2], bb[3]);
+            }
+          }
+        }
+      }
+      if (pass == 1) {
+        if (tid == 0) tma_store_wait_read();                     // the dV store has drained the staging tile
+        __syncthreads();
+      }
+      // accumulators -> staging tile in the TMA 128B-swizzle layout [NCH][32 keys][64]
+#pragma unroll
+      for (int pl = 0; pl < NP; ++pl) {
+        const int dn = warp * NP + pl;
+        if (dn < NPAIR) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nn = 0; nn < 2; ++nn)
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const int row = mt * 16 + g + r * 8;
+                const int col = dn * 16 + nn * 8;
+                const uint32_t off = (uint32_t)((col >> 6) * kv_chunk) + swz(row, col & 63) + (uint32_t)(t4 * 4);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(os_base + off),
+                             "r"(pack_bf16(acc[mt][2 * pl + nn][2 * r], acc[mt][2 * pl + nn][2 * r + 1]))
+                             : "memory");
+              }
+        }
+      }
+      fence_proxy_async();                                       // generic-proxy writes -> visible to the TMA engine
+      __syncthreads();
+      if (tid == 0) {
+        const CUtensorMap* tmO = pass == 0 ? &tmDV : &tmDK;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tma_store_3d(tmO, os_base + c * kv_chunk, h * dh + c * 64, key0, b);
+        tma_store_commit();
+      }
+    }
+    // the barrier inside pass 1 ordered every warp's reads of stage st, Ps and dSs (pass 0 and the S / dP / dQ
+    // products) before this point only for pass 0; close the tile for pass 1's operand reads too
+    __syncthreads();
+  }
+  if (tid == 0) tma_store_wait_all();
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = row0 + r * 8;
+    if (row >= Lq) continue;
+    __nv_bfloat16* orow = dq + ((size_t)b * Lq + row) * HD + h * dh;
+#pragma unroll
+    for (int i = 0; i < NCH * 8; ++i)
+      *reinterpret_cast<uint32_t*>(orow + i * 8 + t4 * 2) = pack_bf16(qacc[i][2 * r], qacc[i][2 * r + 1]);
+  }
+}
+
+template <int NCH, int NW>
+static int launch_bwd_fused(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                            const float* lse, void* dq, void* dk, void* dv, int b, int Lq, int Lk, int heads, int ldq,
+                            int ldk, int ldv, float sm_scale, float p, uint64_t seed, uint64_t offset, cudaStream_t st) {
+  const int dh = NCH * 64, HD = heads * dh;
+  const float sl2 = sm_scale * kLog2e;
+  CUtensorMap tq, tdo, tk, tv, tdk, tdv;
+  int rc;
+  if ((rc = xa_make_tmap(&tq, q, b, Lq, HD, ldq, 16 * NW))) return rc;
+  if ((rc = xa_make_tmap(&tdo, d_o, b, Lq, HD, HD, 16 * NW))) return rc;
+  if ((rc = xa_make_tmap(&tk, k, b, Lk, HD, ldk, XA_KT))) return rc;
+  if ((rc = xa_make_tmap(&tv, v, b, Lk, HD, ldv, XA_KT))) return rc;
+  if ((rc = xa_make_tmap(&tdk, dk, b, Lk, HD, HD, XA_KT))) return rc;
+  if ((rc = xa_make_tmap(&tdv, dv, b, Lk, HD, HD, XA_KT))) return rc;
+  const size_t q_pad = ((size_t)NCH * 16 * NW * 128 + 1023) & ~(size_t)1023;
+  const size_t smem = 1024 + 2 * q_pad + 2 * (2 * NCH * XA_KT * 128) + NCH * XA_KT * 128 + 2 * (16 * NW * 64) + 64 +
+                      16 * NW * 4;
+  XTAG_CUDA(cudaFuncSetAttribute(xattn_bwd_fused_kernel<NCH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  xattn_bwd_fused_kernel<NCH, NW><<<b * heads, 32 * NW, smem, st>>>(
+      tq, tk, tv, tdo, tdk, tdv, (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse, (__nv_bfloat16*)dq, Lq, Lk,
+      heads, sl2, sm_scale, p, seed, offset);
+  XTAG_CHECK_LAUNCH();
+  return XTAG_OK;
+}
+
+template <int NCH>
+static int launch_bwd_fused_nch(int nw, const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                const float* lse, void* dq, void* dk, void* dv, int b, int Lq, int Lk, int heads,
+                                int ldq, int ldk, int ldv, float sm_scale, float p, uint64_t seed, uint64_t offset,
+                                cudaStream_t st) {
+  switch (nw) {
+    case 1: return launch_bwd_fused<NCH, 1>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p, seed, offset, st);
+    case 2: return launch_bwd_fused<NCH, 2>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p, seed, offset, st);
+    case 3: return launch_bwd_fused<NCH, 3>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p, seed, offset, st);
+    default: return launch_bwd_fused<NCH, 4>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p, seed, offset, st);
+  }
+}
+
 template <int NCH>
 static int launch_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                       void* dq, void* dk, void* dv, float* delta, int b, int Lq, int Lk, int heads, int ldq, int ldk,
@@ -686,6 +1021,18 @@ static int launch_bwd(const void* q, const void* k, const void* v, const void* o
 int xattn_mma_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                   void* dq, void* dk, void* dv, float* delta_ws, int b, int Lq, int Lk, int heads, int dh, int ldq, int ldk,
                   int ldv, float sm_scale, float p_drop, uint64_t seed, uint64_t offset, cudaStream_t st) {
+  // the single-pass kernel keeps dQ [16 x dh] and one [32 x dh/NW] product tile per warp in registers: shapes whose
+  // accumulators would spill (few warps with a wide head) stay on the two-kernel path
+  const int nw = (Lq + 15) / 16, nch = dh / 64;
+  const int acc_regs = 16 * ((nch * 4 + nw - 1) / nw) + 32 * nch;
+  if ((tc_tune() & kTuneXattnFusedBwd) && acc_regs <= 224) {
+    switch (nch) {
+      case 1: return launch_bwd_fused_nch<1>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+      case 2: return launch_bwd_fused_nch<2>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+      case 3: return launch_bwd_fused_nch<3>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+      default: return launch_bwd_fused_nch<4>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+    }
+  }
   switch (dh / 64) {
     case 1: return launch_bwd<1>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
     case 2: return launch_bwd<2>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
