@@ -60,7 +60,7 @@ uint64_t    xtag_launch_count(void);
  *               row/column log-sum-exps are within 2^60 of each other, exact two-exp path otherwise)
  *   bit 11      K4 backward as ONE single-pass kernel (K and V streamed once, dK/dV by TMA tile stores) instead of
  *               the query-major dQ kernel + key-major dK/dV kernel pair
- * Initial value: environment variable XTAG_TC_TUNE (0 if unset).  set returns the previous value. */
+ * Initial value: environment variable XTAG_TC_TUNE (0x800 if unset).  set returns the previous value. */
 int         xtag_set_tune(int bits);
 int         xtag_get_tune(void);
 int         xtag_prof_enable(int on);

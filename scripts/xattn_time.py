@@ -25,7 +25,23 @@ def timeit(fn, warmup=3, iters=20):
     return e0.elapsed_time(e1) / iters
 
 
+def profile_once():
+    """one forward + backward at b=1024, N=197 with and without dropout (for an ncu capture; the backward kernel is the
+    one XTAG_TC_TUNE selects)"""
+    K = default_kernels()
+    sc = 1 / math.sqrt(192)
+    q = torch.randn(1024, 44, 768, device="cuda", dtype=torch.bfloat16)
+    kv = torch.randn(1024, 197, 1536, device="cuda", dtype=torch.bfloat16)
+    k, v = kv[..., :768], kv[..., 768:]
+    for p in (0.0, 0.1):
+        o, lse = K.xattn_fwd(q, k, v, 4, sc, p, 1, 2)
+        K.xattn_bwd(q, k, v, o, torch.randn_like(o), lse, 4, sc, p, 1, 2)
+    torch.cuda.synchronize()
+
+
 def main():
+    if "--profile" in sys.argv:
+        return profile_once()
     K = default_kernels()
     sc = 1 / math.sqrt(192)
     out = []

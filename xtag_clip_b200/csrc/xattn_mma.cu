@@ -56,6 +56,32 @@ constexpr int XA_KT = 32;        // keys per pipeline stage
 constexpr int kTuneXattnFusedBwd = 0x800;   // xtag_set_tune bit 11: single-pass K4 backward
 constexpr int XA_MAXW = 4;       // up to 64 query rows
 
+// Dropout keep-bits for this thread's elements of a [16 rows x XA_KT keys] accumulator tile (query-major kernels):
+// element (row r in {row0, row0+8}, n8 tile i, column 2*t4 + c) <-> bit (2*i + c) of bits[r].
+// A Philox block covers 4 consecutive keys = the columns of two neighbouring lanes (t4, t4^1) of one n8 tile: the even
+// lane computes the block of tile 2*ip, the odd lane the block of tile 2*ip + 1, and they swap keep-bits with one
+// shuffle -- 4 elements per Philox call instead of 1.  key0 (first key of the tile) is a multiple of 4.
+__device__ __forceinline__ void dropout_bits_tile(uint32_t (&bits)[2], uint64_t seed, uint64_t offset, uint64_t row_id0,
+                                                  int key0, int kblocks, uint32_t thr, int t4) {
+  const int odd = t4 & 1;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int ip = 0; ip < XA_KT / 16; ++ip) {
+      const int i_mine = 2 * ip + odd;                               // the n8 tile whose block this lane computes
+      const int kblk = (key0 >> 2) + 2 * i_mine + (t4 >> 1);
+      const uint32_t own = philox_keep4(seed, offset, row_id0 + (uint64_t)(r * 8), kblk, kblocks, thr);
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, own, 1);
+      const uint32_t even_tile = odd ? other : own;                  // block of tile 2*ip   (computed by the even lane)
+      const uint32_t odd_tile = odd ? own : other;                   // block of tile 2*ip+1 (computed by the odd lane)
+      acc |= ((even_tile >> (2 * odd)) & 3u) << (2 * (2 * ip));
+      acc |= ((odd_tile >> (2 * odd)) & 3u) << (2 * (2 * ip + 1));
+    }
+    bits[r] = acc;
+  }
+}
+
 // NCH = dh / 64
 template <int NCH>
 __global__ void __launch_bounds__(32 * XA_MAXW)
@@ -119,6 +145,7 @@ xattn_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int qrow = warp * 16 + (lane & 15);                 // ldmatrix row supplied by this lane (A operand)
   const int row0 = warp * 16 + g;                           // accumulator rows owned: row0 and row0 + 8
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const uint32_t drop_thr = philox_drop_threshold(p_drop);
 
   for (int t = 0; t < num_tiles; ++t) {
     const int st = t & 1;
@@ -186,15 +213,13 @@ xattn_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (p_drop > 0.f) {
       // dropout acts on the normalised probabilities; the normaliser is linear, so masking the unnormalised
       // numerators (after the row sum above) is equivalent
+      uint32_t keep[2];
+      dropout_bits_tile(keep, seed, offset, (uint64_t)bh * Lq + row0, key0, (Lk + 3) >> 2, drop_thr, t4);
 #pragma unroll
       for (int i = 0; i < XA_KT / 8; ++i) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int key = key0 + i * 8 + t4 * 2 + (j & 1);
-          const int row = row0 + ((j >> 1) << 3);
-          const uint64_t idx = ((uint64_t)bh * Lq + row) * Lk + key;
-          sacc[i][j] = philox_keep(seed, offset, idx, p_drop) ? sacc[i][j] * keep_scale : 0.f;
-        }
+        for (int j = 0; j < 4; ++j)
+          sacc[i][j] = ((keep[j >> 1] >> (2 * i + (j & 1))) & 1u) ? sacc[i][j] * keep_scale : 0.f;
       }
     }
 #pragma unroll
@@ -313,6 +338,53 @@ int xattn_mma_fwd(const void* q, const void* k, const void* v, void* o, float* l
 }
 
 
+
+// delta_r = sum_c dO[r,c] * O[r,c] for this warp's 16 query rows.  O comes straight from global memory (it is needed
+// nowhere else): all 16 row loads of a lane are issued back to back (one 16-byte unit per lane and row), so the warp
+// pays ONE global round trip instead of sixteen dependent ones; dO is read from its TMA-swizzled smem tile.
+// Phase 1 (before the wait on the Q/dO barrier) fills ov, phase 2 (after it) reduces.
+template <int NCH>
+__device__ __forceinline__ void delta_load_o(uint4 (&ov)[16], const __nv_bfloat16* __restrict__ o, int warp, int lane,
+                                             int b, int h, int Lq, int HD) {
+  const bool act = lane < NCH * 8;
+#pragma unroll
+  for (int rr = 0; rr < 16; ++rr) {
+    const int row = warp * 16 + rr;
+    ov[rr] = make_uint4(0u, 0u, 0u, 0u);
+    if (act && row < Lq)
+      ov[rr] = __ldg(reinterpret_cast<const uint4*>(o + ((size_t)b * Lq + row) * HD + h * (NCH * 64) + lane * 8));
+  }
+}
+template <int NCH>
+__device__ __forceinline__ void delta_reduce(const uint4 (&ov)[16], uint32_t do_base, int qrows, int warp, int lane,
+                                             int Lq, float* delta_s, float* delta_g) {
+  const bool act = lane < NCH * 8;
+#pragma unroll
+  for (int rr = 0; rr < 16; ++rr) {
+    const int row = warp * 16 + rr;
+    float sacc = 0.f;
+    if (act) {
+      uint32_t d0, d1, d2, d3;
+      const uint32_t addr = do_base + (uint32_t)((lane >> 3) * qrows * 128) + swz(row, (lane & 7) * 8);
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(d1), "=r"(d2), "=r"(d3) : "r"(addr));
+      const uint32_t dw[4] = {d0, d1, d2, d3};
+      const uint32_t ow[4] = {ov[rr].x, ov[rr].y, ov[rr].z, ov[rr].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[k]));
+        const float2 d2f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[k]));
+        sacc = fmaf(a.x, d2f.x, fmaf(a.y, d2f.y, sacc));
+      }
+    }
+    sacc = warp_sum(sacc);
+    if (lane == 0) {
+      delta_s[row] = sacc;
+      if (delta_g != nullptr && row < Lq) delta_g[row] = sacc;
+    }
+  }
+  __syncwarp();
+}
+
 // =============================================================================================================
 // Backward.  Two kernels, each a forward-shaped pipeline (TMA tiles, ldmatrix, mma.sync):
 //   xattn_bwd_dq_kernel   query-major, one CTA per (sample, head): recompute S and dP = dO V^T tile by tile,
@@ -377,26 +449,12 @@ xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     issue_tile(0);
   }
-  // delta_r = sum_c dO[r,c] * O[r,c] for this warp's 16 rows (straight from global memory, once)
-  for (int rr = 0; rr < 16; ++rr) {
-    const int row = warp * 16 + rr;
-    float sacc = 0.f;
-    if (row < Lq) {
-      const __nv_bfloat16* op = o + ((size_t)b * Lq + row) * HD + h * dh;
-      const __nv_bfloat16* dp = d_o + ((size_t)b * Lq + row) * HD + h * dh;
-      for (int c = lane * 2; c < dh; c += 64) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(op + c));
-        const float2 d2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp + c));
-        sacc = fmaf(a.x, d2.x, fmaf(a.y, d2.y, sacc));
-      }
-    }
-    sacc = warp_sum(sacc);
-    if (lane == 0) {
-      delta_s[row] = sacc;
-      if (row < Lq) delta[(size_t)bh * Lq + row] = sacc;
-    }
+  {
+    uint4 ov[16];
+    delta_load_o<NCH>(ov, o, warp, lane, b, h, Lq, HD);
+    mbar_wait(smem_u32(&bars[0]), 0);
+    delta_reduce<NCH>(ov, smem_u32(dOs), QROWS, warp, lane, Lq, delta_s, delta + (size_t)bh * Lq);
   }
-  __syncwarp();
 
   const int g = lane >> 2, t4 = lane & 3;
   const int row0 = warp * 16 + g;
@@ -417,6 +475,7 @@ xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t q_base = smem_u32(Qs), do_base = smem_u32(dOs);
   const int qrow = warp * 16 + (lane & 15);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const uint32_t drop_thr = philox_drop_threshold(p_drop);
 
   for (int t = 0; t < num_tiles; ++t) {
     const int st = t & 1;
@@ -449,6 +508,8 @@ xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
     const int key0 = t * XA_KT;
+    uint32_t keep[2] = {0xffffffffu, 0xffffffffu};
+    if (p_drop > 0.f) dropout_bits_tile(keep, seed, offset, (uint64_t)bh * Lq + row0, key0, (Lk + 3) >> 2, drop_thr, t4);
 #pragma unroll
     for (int i = 0; i < XA_KT / 8; ++i) {
 #pragma unroll
@@ -456,11 +517,7 @@ xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int key = key0 + i * 8 + t4 * 2 + (j & 1);
         const int r = j >> 1;
         float p = (key < Lk) ? fast_exp2(fmaf(sacc[i][j], sl2, -lse2[r])) : 0.f;
-        float m = 1.f;
-        if (p_drop > 0.f) {
-          const uint64_t idx = ((uint64_t)bh * Lq + (row0 + r * 8)) * Lk + key;
-          m = philox_keep(seed, offset, idx, p_drop) ? keep_scale : 0.f;
-        }
+        const float m = ((keep[r] >> (2 * i + (j & 1))) & 1u) ? keep_scale : 0.f;
         sacc[i][j] = p * (pacc[i][j] * m - dl[r]) * sm_scale;        // dS (w.r.t. q.k before the 1/sqrt(dh) scale)
       }
     }
@@ -551,6 +608,7 @@ xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t q_base = smem_u32(Qs), do_base = smem_u32(dOs), k_base = smem_u32(Ks), v_base = smem_u32(Vs);
   const int krow_a = warp * 16 + (lane & 15);                    // A-operand row (key) supplied by this lane
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const uint32_t drop_thr = philox_drop_threshold(p_drop);
 
   // S^T = K_w Q^T and dP^T = V_w dO^T : 16 keys x QROWS queries
   float st[2 * NQT][4], pt[2 * NQT][4];
@@ -587,8 +645,8 @@ xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float p = fast_exp2(fmaf(st[i][j], sl2, -lse2_s[qi]));
       float m = 1.f;
       if (p_drop > 0.f) {
-        const uint64_t idx = ((uint64_t)bh * Lq + qi) * Lk + key;
-        m = (qi < Lq && key < Lk && philox_keep(seed, offset, idx, p_drop)) ? keep_scale : 0.f;
+        m = (qi < Lq && key < Lk && philox_keep(seed, offset, (uint64_t)bh * Lq + qi, key, (Lk + 3) >> 2, drop_thr))
+                ? keep_scale : 0.f;
       }
       st[i][j] = p * (pt[i][j] * m - delta_s[qi]) * sm_scale;    // dS^T
       pt[i][j] = p * m;                                          // dropped probabilities Pd^T
@@ -723,23 +781,12 @@ xattn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
     issue_tile(0);
   }
-  // delta_r = sum_c dO[r,c] * O[r,c] for this warp's 16 rows (O is only needed here: straight from global memory)
-  for (int rr = 0; rr < 16; ++rr) {
-    const int row = warp * 16 + rr;
-    float sacc = 0.f;
-    if (row < Lq) {
-      const __nv_bfloat16* op = o + ((size_t)b * Lq + row) * HD + h * dh;
-      const __nv_bfloat16* dp = d_o + ((size_t)b * Lq + row) * HD + h * dh;
-      for (int c = lane * 2; c < dh; c += 64) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(op + c));
-        const float2 d2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dp + c));
-        sacc = fmaf(a.x, d2.x, fmaf(a.y, d2.y, sacc));
-      }
-    }
-    sacc = warp_sum(sacc);
-    if (lane == 0) delta_s[row] = sacc;
+  {
+    uint4 ov[16];
+    delta_load_o<NCH>(ov, o, warp, lane, b, h, Lq, HD);
+    mbar_wait(smem_u32(&bars[0]), 0);
+    delta_reduce<NCH>(ov, smem_u32(dOs), QROWS, warp, lane, Lq, delta_s, nullptr);
   }
-  __syncwarp();
 
   const int g = lane >> 2, t4 = lane & 3;
   const int row0 = warp * 16 + g;
@@ -761,6 +808,7 @@ xattn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t ps_base = smem_u32(Ps), ds_base = smem_u32(dSs), os_base = smem_u32(Os);
   const int qrow = warp * 16 + (lane & 15);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const uint32_t drop_thr = philox_drop_threshold(p_drop);
 
   for (int t = 0; t < num_tiles; ++t) {
     const int st = t & 1;
@@ -795,6 +843,8 @@ xattn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
     }
     // ---- elementwise: sacc <- dS, pacc <- dropped probabilities ----
+    uint32_t keep[2] = {0xffffffffu, 0xffffffffu};
+    if (p_drop > 0.f) dropout_bits_tile(keep, seed, offset, (uint64_t)bh * Lq + row0, key0, (Lk + 3) >> 2, drop_thr, t4);
 #pragma unroll
     for (int i = 0; i < XA_KT / 8; ++i) {
 #pragma unroll
@@ -802,11 +852,7 @@ xattn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int key = key0 + i * 8 + t4 * 2 + (j & 1);
         const int r = j >> 1;
         const float p = (key < Lk) ? fast_exp2(fmaf(sacc[i][j], sl2, -lse2[r])) : 0.f;
-        float m = 1.f;
-        if (p_drop > 0.f) {
-          const uint64_t idx = ((uint64_t)bh * Lq + (row0 + r * 8)) * Lk + key;
-          m = philox_keep(seed, offset, idx, p_drop) ? keep_scale : 0.f;
-        }
+        const float m = ((keep[r] >> (2 * i + (j & 1))) & 1u) ? keep_scale : 0.f;
         sacc[i][j] = p * (pacc[i][j] * m - dl[r]) * sm_scale;    // dS (w.r.t. q.k before the 1/sqrt(dh) scale)
         pacc[i][j] = p * m;
       }

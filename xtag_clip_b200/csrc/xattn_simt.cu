@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(256) xattn_fwd_simt_kernel(const T* __restrict
     for (int n = lane; n < Lk; n += 32) {
       float p = exp2f(Ss[r * Lk + n] - mx) * inv;
       if (p_drop > 0.f) {
-        const uint64_t idx = ((uint64_t)bh * Lq + r) * Lk + n;
-        p = philox_keep(seed, offset, idx, p_drop) ? p * keep_scale : 0.f;
+        p = philox_keep(seed, offset, (uint64_t)bh * Lq + r, n, (Lk + 3) >> 2, philox_drop_threshold(p_drop))
+                ? p * keep_scale : 0.f;
       }
       Ss[r * Lk + n] = p;
     }
@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(256) xattn_bwd_simt_kernel(const T* __restrict
     const float p = exp2f(s * sl2 - lse[(size_t)bh * Lq + r] * kLog2e);
     float m = 1.f;
     if (p_drop > 0.f) {
-      const uint64_t idx = ((uint64_t)bh * Lq + r) * Lk + n;
-      m = philox_keep(seed, offset, idx, p_drop) ? keep_scale : 0.f;
+      m = philox_keep(seed, offset, (uint64_t)bh * Lq + r, n, (Lk + 3) >> 2, philox_drop_threshold(p_drop))
+              ? keep_scale : 0.f;
     }
     Ps[r * Lk + n] = p * m;
     dSs[r * Lk + n] = p * (dp * m - delta[r]) * sm_scale;   // d(score before scale) folded with sm_scale
