@@ -181,6 +181,8 @@ class ClockSampler:
 
 
 def run_ours(args):
+    from xtag_clip_b200._cuda_probe import wait_for_cuda
+    wait_for_cuda()
     import torch
     import torch.distributed as dist
     import xtag_clip_b200 as xt

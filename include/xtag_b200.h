@@ -111,6 +111,19 @@ int xtag_clip_fwd_block(const void* A, const void* Bm_blk, int dtype, int M, int
                         float* row_part, float* col_part, int col_ld, float* diag, void* stream);
 int xtag_lse_reduce_log2(const float* parts, int P, int n, float* out, void* stream);
 
+/* K1 fused with the feature exchange: ONE persistent launch over the whole gather buffer Bm_all [N, D] whose nblk
+ * column blocks (blk_cols rows each, a multiple of 256) are filled concurrently by copy-engine pulls from the peers.
+ * The kernel visits the blocks in order_host[] and, for a block with wait_host[k] != 0, starts loading its tiles only
+ * once ready_flags[block] == *epoch (a 4-byte copy the exchange enqueues right behind the block's data on the same copy
+ * stream), so the transfer overlaps the math tile by tile with no launch per block.  Partials as xtag_clip_fwd_block:
+ * row_part [2*ceil(N/256)][M], col_part [ceil(M/128)][col_ld]; finish with two xtag_lse_reduce_log2 calls.
+ * label_offset is the global column of row 0's label (b*rank).  tcgen05 path only. */
+int xtag_clip_fwd_stream(const void* A, const void* Bm_all, int dtype, int M, int N, int D,
+                         const float* scale, int label_offset,
+                         const int* order_host, const int* wait_host, int nblk, int blk_cols,
+                         const int* ready_flags, const int* epoch,
+                         float* row_part, float* col_part, int col_ld, float* diag, void* stream);
+
 /* out[j] = log sum_w exp(parts[w*N + j]): merges the per-rank partial column LSEs after the
  * all-gather (the one exchange step of the sharded loss). */
 int xtag_lse_combine(const float* parts, int W, int N, float* out, void* stream);

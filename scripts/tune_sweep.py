@@ -23,7 +23,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32768)
     ap.add_argument("--dim", type=int, default=1024)
-    ap.add_argument("--iters", type=int, default=6)
+    ap.add_argument("--iters", type=int, default=4)
+    ap.add_argument("--rounds", type=int, default=8)
+    ap.add_argument("--heat", type=float, default=3.0, help="seconds of load before the first measurement")
     ap.add_argument("--tunes", default="0x0,0x400,0x4,0x8,0xc,0x100,0x200,0x308,0x10c")
     args = ap.parse_args()
     import torch
@@ -41,36 +43,54 @@ def main():
     w = (0.5 / B, 0.5 / B, 1.0 / B)
     names = {0: "fwd", 1: "ds", 2: "gemm"}
     out_path = os.path.join(ROOT, "gpurun_out", "tune_sweep.jsonl")
+    tunes = [int(t, 0) for t in args.tunes.split(",")]
+
+    def one_step():
+        row, col, diag = K.clip_fwd(I, T, s, 0)
+        dA, dB, ds = K.clip_bwd(I, T, s, 0, row, col, *w, gout, True, True, torch.bfloat16)
+        return row, col, diag, dA, dB, ds
+
+    # The kernels run at the board's power cap: clocks sag from burst to a sustained level within ~2 s of load, so a
+    # sequential A/B is dominated by drift.  Warm the GPU into the sustained state first, then visit the settings
+    # round-robin and average over the rounds.
+    t_end = __import__("time").time() + args.heat
+    while __import__("time").time() < t_end:
+        for _ in range(10):
+            one_step()
+        torch.cuda.synchronize()
+    acc = {t: dict(ms=[], per={}) for t in tunes}
     ref = None
-    for tune in [int(t, 0) for t in args.tunes.split(",")]:
-        lib.xtag_set_tune(tune)
-        for _ in range(2):
-            row, col, diag = K.clip_fwd(I, T, s, 0)
-            dA, dB, ds = K.clip_bwd(I, T, s, 0, row, col, *w, gout, True, True, torch.bfloat16)
-        torch.cuda.synchronize()
-        lib.xtag_prof_enable(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.iters):
-            row, col, diag = K.clip_fwd(I, T, s, 0)
-            dA, dB, ds = K.clip_bwd(I, T, s, 0, row, col, *w, gout, True, True, torch.bfloat16)
-        e1.record()
-        torch.cuda.synchronize()
-        cap = 16 * args.iters + 16
-        tags, tms, work = (ctypes.c_int * cap)(), (ctypes.c_float * cap)(), (ctypes.c_double * cap)()
-        n = lib.xtag_prof_read(tags, tms, work, cap)
-        lib.xtag_prof_enable(0)
-        per = {}
-        for i in range(n):
-            per.setdefault(names.get(tags[i], str(tags[i])), []).append(tms[i])
-        loss = float(K.clip_loss(row, diag, col, 0))
-        chk = (float(dA.float().abs().sum()), float(dB.float().abs().sum()), float(ds))
-        if ref is None:
-            ref = chk
-        rec = dict(tune=hex(tune), batch=B, dim=D, ms_per_step=e0.elapsed_time(e1) / args.iters,
-                   kernels_ms={k: sum(v) / len(v) for k, v in per.items()},
-                   kernels_min_ms={k: min(v) for k, v in per.items()}, loss=loss,
-                   grad_l1_vs_first=[c / r if r else None for c, r in zip(chk, ref)])
+    chk_of = {}
+    for rnd in range(args.rounds):
+        for tune in tunes:
+            lib.xtag_set_tune(tune)
+            one_step()
+            torch.cuda.synchronize()
+            lib.xtag_prof_enable(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.iters):
+                row, col, diag, dA, dB, ds = one_step()
+            e1.record()
+            torch.cuda.synchronize()
+            cap = 16 * args.iters + 16
+            tags, tms, work = (ctypes.c_int * cap)(), (ctypes.c_float * cap)(), (ctypes.c_double * cap)()
+            n = lib.xtag_prof_read(tags, tms, work, cap)
+            lib.xtag_prof_enable(0)
+            for i in range(n):
+                acc[tune]["per"].setdefault(names.get(tags[i], str(tags[i])), []).append(tms[i])
+            acc[tune]["ms"].append(e0.elapsed_time(e1) / args.iters)
+            if rnd == 0:
+                chk = (float(K.clip_loss(row, diag, col, 0)), float(dA.float().abs().sum()),
+                       float(dB.float().abs().sum()), float(ds))
+                ref = ref or chk
+                chk_of[tune] = [c / r if r else None for c, r in zip(chk, ref)]
+    for tune in tunes:
+        a = acc[tune]
+        rec = dict(tune=hex(tune), batch=B, dim=D, rounds=args.rounds, iters=args.iters,
+                   ms_per_step=sum(a["ms"]) / len(a["ms"]), ms_per_step_min=min(a["ms"]),
+                   kernels_ms={k: sum(v) / len(v) for k, v in a["per"].items()},
+                   kernels_min_ms={k: min(v) for k, v in a["per"].items()}, loss_grad_vs_first=chk_of[tune])
         line = json.dumps(rec)
         print(line, flush=True)
         if os.path.isdir(os.path.dirname(out_path)):

@@ -18,6 +18,9 @@ def pytest_collection_modifyitems(config, items):
     """GPU tests are skipped (not failed) where no CUDA device exists, so a plain
     `pytest tests/` stays green on the CPU build box."""
     try:
+        from xtag_clip_b200._cuda_probe import has_device_nodes, wait_for_cuda
+        if has_device_nodes():
+            wait_for_cuda()          # a fresh GPU box can fail its first cuInit; the failure is sticky per process
         import torch
         has_cuda = torch.cuda.is_available()
     except Exception:

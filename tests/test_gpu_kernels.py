@@ -181,7 +181,7 @@ def test_clip_wide_dynamic_range(MK):
         assert rel_err(dA, dAm) < 2e-2 and rel_err(dB, dBm) < 2e-2
 
 
-@pytest.mark.parametrize("tune", [0x000, 0x400, 0x008, 0x004, 0x300, 0x30c])
+@pytest.mark.parametrize("tune", [0x000, 0x400, 0x008, 0x004, 0x300, 0x30c, 0x4000, 0x8000, 0x4400])
 @pytest.mark.parametrize("M,N,D,off,scale", [(130, 300, 72, 100, 14.285714), (512, 1024, 512, 256, 100.0),
                                              (1024, 1024, 1024, 0, 30.0)])
 def test_tc_tune_bits_parity(MK, tune, M, N, D, off, scale):
@@ -272,6 +272,63 @@ def test_clip_fwd_blocks_deferred_reductions(K, MK, M, D, blocks, own):
     assert rel_err(row, rm) < 2e-5 and rel_err(col, cm) < 2e-5 and rel_err(diag, dm) < 2e-5
     r1, c1, d1 = K.clip_fwd(Ac, Bc, sc, off)
     assert rel_err(row, r1) < 1e-6 and rel_err(col, c1) < 1e-6 and torch.equal(diag, d1)
+
+
+@pytest.mark.parametrize("tune", [0x4000, 0x8000])
+@pytest.mark.parametrize("M,N,Kd", [(256, 512, 128), (512, 768, 4096), (4096, 1024, 4096), (1024, 1000, 1000), (384, 256, 64)])
+def test_tc_gemm_cluster_multicast(K, tune, M, N, Kd):
+    """Thread-block clusters along M with the shared B tile TMA-multicast (tune bits 14 / 15), all three operand
+    layouts; shapes whose m-tile count is not a multiple of the cluster size fall back to smaller clusters."""
+    old = K.lib.xtag_set_tune(tune)
+    try:
+        g = torch.Generator().manual_seed(M + N + Kd)
+        A = torch.randn(M, Kd, generator=g).bfloat16().cuda()
+        B = torch.randn(N, Kd, generator=g).bfloat16().cuda()
+        ref = A.float() @ B.float().T
+        assert rel_err(K.tc_gemm_nt(A, B, torch.float32, 1.0), ref) < 2e-5
+        if N % 8 == 0:
+            Bkn = B.T.contiguous()
+            assert rel_err(K.tc_gemm(A, Bkn, False, True, torch.float32), ref) < 2e-5
+            if M % 8 == 0:
+                assert rel_err(K.tc_gemm(A.T.contiguous(), Bkn, True, True, torch.float32), ref) < 2e-5
+    finally:
+        K.lib.xtag_set_tune(old)
+
+
+@pytest.mark.parametrize("M,D,blk,order", [(256, 256, 256, [1, 0, 2, 3]), (384, 512, 512, [2, 3, 0, 1]),
+                                            (1024, 1024, 1024, [0, 1]), (130, 64, 256, [3, 2, 1, 0, 4])])
+def test_clip_fwd_stream_flag_gated(K, MK, M, D, blk, order):
+    """xtag_clip_fwd_stream: one persistent launch over a gather buffer whose column blocks are released by ready
+    flags.  The flags are written from a second stream AFTER the kernel was launched (behind a delay and behind the
+    copy that fills the block), so the kernel really has to wait for them; the result must equal the plain forward."""
+    nblk = len(order)
+    N = nblk * blk
+    I, T = feats(M + D + nblk, max(M, N), D, corr=0.2, dtype=torch.bfloat16)
+    A = I[:M].contiguous()
+    own = order[0]
+    off = own * blk if own * blk + M <= N else 0
+    Bm = torch.roll(T[:N], shifts=off, dims=0).contiguous()
+    s = torch.tensor([25.0])
+    Ac, sc = A.cuda(), s.cuda()
+    src = Bm.cuda()
+    gather = torch.zeros_like(src)                       # blocks land here one by one
+    flags = torch.zeros(nblk, dtype=torch.int32, device="cuda")
+    epoch = torch.full((1,), 7, dtype=torch.int32, device="cuda")
+    gather[own * blk:(own + 1) * blk].copy_(src[own * blk:(own + 1) * blk])
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    wait = [False] + [True] * (nblk - 1)
+    # the block copies are enqueued first (as the exchange does): work submitted AFTER the persistent kernel could sit
+    # behind it in a shared hardware queue and never start
+    with torch.cuda.stream(side):
+        for p in order[1:]:
+            torch.cuda._sleep(1_000_000)                  # ~0.5 ms per block: the kernel is spinning on this flag
+            gather[p * blk:(p + 1) * blk].copy_(src[p * blk:(p + 1) * blk], non_blocking=True)
+            flags[p:p + 1].copy_(epoch, non_blocking=True)
+    row, col, diag = K.clip_fwd_stream(Ac, gather, sc, off, order, wait, blk, flags, epoch)
+    torch.cuda.synchronize()
+    rm, cm, dm = MK.clip_fwd(A, Bm, s, off)
+    assert rel_err(row, rm) < 2e-5 and rel_err(col, cm) < 2e-5 and rel_err(diag, dm) < 2e-5
 
 
 def test_lse_combine(K):

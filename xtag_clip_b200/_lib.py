@@ -34,6 +34,9 @@ SIGNATURES = {
     "xtag_clip_fwd_block_parts": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "xtag_clip_fwd_block": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                     c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "xtag_clip_fwd_stream": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                     c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "xtag_lse_reduce_log2": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "xtag_lse_combine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "xtag_lse_combine_ptrs": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -22,6 +22,9 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
 void tc_fwd_block_parts(int M, int N, int* row_parts, int* col_parts);
 int tc_clip_fwd_block(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
                       float* row_part, float* col_part, int col_ld, float* diag, cudaStream_t st);
+int tc_clip_fwd_stream(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
+                       const int* order, const int* wait, int nblk, int blk_cols, const int* ready_flags,
+                       const int* epoch, float* row_part, float* col_part, int col_ld, float* diag, cudaStream_t st);
 int launch_lse_reduce(const float* parts, int P, int n, float in_mul, float out_mul, float* out, cudaStream_t st);
 
 // tcgen05 path needs bf16 operands whose rows are 16-byte multiples (TMA global stride rule)
@@ -119,4 +122,25 @@ extern "C" int xtag_clip_fwd_block(const void* A, const void* Bm, int dtype, int
 extern "C" int xtag_lse_reduce_log2(const float* parts, int P, int n, float* out, void* stream) {
   XTAG_REQUIRE(parts && out && P > 0 && n > 0, XTAG_ERR_INVALID, "lse_reduce_log2: bad arguments");
   return launch_lse_reduce(parts, P, n, 1.f, kLn2, out, (cudaStream_t)stream);
+}
+
+// ---- streamed forward: ONE launch consumes the gather buffer block by block as the peers' features land ----------
+extern "C" int xtag_clip_fwd_stream(const void* A, const void* Bm_all, int dtype, int M, int N, int D,
+                                    const float* scale, int label_offset, const int* order_host,
+                                    const int* wait_host, int nblk, int blk_cols, const int* ready_flags,
+                                    const int* epoch, float* row_part, float* col_part, int col_ld, float* diag,
+                                    void* stream) {
+  XTAG_REQUIRE(A && Bm_all && scale && order_host && wait_host && row_part && col_part && diag, XTAG_ERR_INVALID,
+               "clip_fwd_stream: null pointer");
+  XTAG_REQUIRE(M > 0 && N > 0 && D > 0 && col_ld >= N, XTAG_ERR_INVALID, "clip_fwd_stream: bad shape");
+  XTAG_REQUIRE(tc_eligible(dtype, D), XTAG_ERR_UNSUPPORTED, "clip_fwd_stream: tcgen05 path only (bf16, D %% 8 == 0)");
+  XTAG_REQUIRE(label_offset >= 0 && (long)label_offset + M <= (long)N, XTAG_ERR_INVALID,
+               "clip_fwd_stream: labels [%d, %d) fall outside the %d columns", label_offset, label_offset + M, N);
+  bool any_wait = false;
+  for (int k = 0; k < nblk && k < 16; ++k) any_wait |= wait_host[k] != 0;
+  XTAG_REQUIRE(!any_wait || (ready_flags && epoch), XTAG_ERR_INVALID, "clip_fwd_stream: waiting blocks need flags");
+  int rc = xtag_device_check();
+  if (rc) return rc;
+  return tc_clip_fwd_stream(A, Bm_all, M, N, D, scale, label_offset, order_host, wait_host, nblk, blk_cols, ready_flags,
+                            epoch, row_part, col_part, col_ld, diag, (cudaStream_t)stream);
 }

@@ -67,22 +67,47 @@ struct EpiParams {
   int c_is_bf16;
   float alpha;            // C = alpha * (alpha_p ? *alpha_p : 1) * acc
   const float* alpha_p;
+  // streamed forward (EPI_LSE over a gather buffer that fills up block by block): column block k of blk_tiles n tiles
+  // is is one slab of the tile schedule, slabs are visited in arrival order; ready_flags[blk] == *epoch_p once block blk has landed
+  const int* ready_flags; // device [nblk] or nullptr
+  const int* epoch_p;     // device scalar
+  int blk_tiles;          // n tiles per column block (0: not streamed)
+  int blk_order[16];      // slab s of the schedule works on column block blk_order[s]
+  int blk_wait[16];       // 1: slab s must wait for its ready flag
   // all epilogues: runtime tuning bits (xtag_set_tune): [0,8) L2 prefetch distance in k-blocks (0 = off),
   // bit 8 dS tile stores carry an L2 evict_first hint, bit 9 operand loads carry an L2 evict_last hint,
   // bit 10 forces the two-exponential dS path
   int tune;
 };
 constexpr int kTunePrefetchMask = 0xff, kTuneStoreEvictFirst = 0x100, kTuneLoadEvictLast = 0x200,
-              kTuneDsTwoExp = 0x400;
+              kTuneDsTwoExp = 0x400,
+              kTuneCluster2 = 0x4000,       // clusters of 2 CTAs along M with TMA multicast of the shared B tile
+              kTuneCluster4 = 0x8000,       // clusters of 4
+              kTuneDbgNoDsStore = 0x1000,   // diagnostics only (wrong results): dS tile neither staged nor stored
+              kTuneDbgNoDsTma = 0x2000;     // diagnostics only (wrong results): dS tile staged in smem, TMA store skipped
 
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& m_blk, int& n_blk) {
-  const int per_group = kGroupM * num_n;
-  const int group = tile / per_group;
+// Static tile schedule.  Tiles are ordered  n-slab  >  group of kGroupM m tiles  >  n tile inside the slab  >  m tile
+// inside the group, so that at any time the CTAs work on a [kGroupM m tiles] x [~#SM / kGroupM n tiles] patch (operand
+// tiles shared through L2 by the CTAs of a wave), a group's A tiles are re-used across one slab, and a slab's B tiles are
+// re-used by every group before the schedule moves on: with `slab` n tiles per slab the B slab (slab * BN rows) stays
+// L2-resident while the groups stream past it even when the kernel also writes a large output (the dS producer writes
+// 2*BM*BN bytes per tile; without slabs every group pass re-fetched the whole B matrix from HBM and each k-block load
+// paid DRAM latency, which the 4-stage ring cannot hide: measured 77 % vs 95 % tensor-pipe activity).
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int slab, const int* slab_order, int& m_blk,
+                                            int& n_blk, int* slab_idx = nullptr) {
+  const int per_slab = num_m * slab;
+  const int s = tile / per_slab;
+  if (slab_idx) *slab_idx = s;
+  const int n0 = (slab_order ? slab_order[s] : s) * slab;
+  const int ns = min(slab, num_n - n0);
+  const int r = tile - s * per_slab;
+  const int per_group = kGroupM * ns;
+  const int group = r / per_group;
   const int first_m = group * kGroupM;
   const int gsize = min(num_m - first_m, kGroupM);
-  const int in = tile - group * per_group;
+  const int in = r - group * per_group;
   m_blk = first_m + in % gsize;
-  n_blk = in / gsize;
+  n_blk = n0 + in / gsize;
 }
 
 // Transpose-reduce over the 32 lanes of a warp: on entry x[j] is lane-local value for column j; on exit
@@ -309,7 +334,7 @@ __device__ __forceinline__ float ds_tile(const EpiParams& ep, const CUtensorMap*
     // ---- store: 32 rows x 64 B of bf16 through shared memory and one TMA tile store per warp and chunk.
     // Direct STG would write 16 B per 128-B line per instruction (32 L2 requests per warp instruction, measured as
     // the kernel's dominant stall); the TMA store issues full 64-B row segments and clips ragged edges itself.
-    {
+    if (!(ep.tune & kTuneDbgNoDsStore)) {
       if (lane == 0) tma_store_wait_read();                 // previous tile store has drained this buffer
       __syncwarp();
 #pragma unroll
@@ -323,7 +348,7 @@ __device__ __forceinline__ float ds_tile(const EpiParams& ep, const CUtensorMap*
       }
       fence_proxy_async();                                  // generic-proxy writes -> visible to the TMA engine
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !(ep.tune & kTuneDbgNoDsTma)) {
         if (store_policy) tma_store_2d_hint(tmC, ostage, c0, row_blk, store_policy);
         else              tma_store_2d(tmC, ostage, c0, row_blk);
         tma_store_commit();
@@ -382,10 +407,15 @@ __device__ __forceinline__ void store_tile(const EpiParams& ep, uint32_t taddr, 
 // A_MN / B_MN: the operand is stored "MN-major": global tensor [K rows][M or N contiguous] (e.g. dS read as the
 // A operand of dB = dS^T A, or row-major features read as the B operand [N=D][K] of dA = dS Bm).  TMA then loads
 // 64-element (128 B) wide boxes of BK rows; UMMA reads them through an MN-major 128B-swizzle descriptor.
-template <int EPI, bool A_MN, bool B_MN>
+// CL = thread-block cluster size along M (1, 2 or 4): the CL CTAs of a cluster work on CL consecutive m tiles of the
+// SAME n tile, so the B operand tile is shared: each CTA fetches 1/CL of it and TMA-multicasts that slice into the
+// shared memory of all CL CTAs.  Per CTA the TMA unit then moves BM + BN/CL rows per k-block instead of BM + BN and
+// the L2 -> SM operand traffic drops by the same factor (measured: the TMA/L2 request rate, not the tensor pipe, is
+// what the 128x256 tiles saturate first; an added L2 prefetch stream slows the kernels by 1.4x).
+template <int EPI, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, int M, int N, int K, EpiParams ep) {
+               const __grid_constant__ CUtensorMap tmC, int M, int N, int K, const __grid_constant__ EpiParams ep) {
   // 1024-byte alignment is required by the 128B-swizzle atoms; align inside the shared window with pointer
   // arithmetic on the __shared__ array itself so the compiler keeps emitting LDS/STS (a uintptr_t round trip turns
   // every access into a generic LD/ST: measured as "lg" stalls in the epilogue)
@@ -408,6 +438,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = (K + BK - 1) / BK;
+  const int slab_req = (ep.tune >> 16) & 0xff;                    // n tiles per slab of the tile schedule (0: one slab)
+  const bool streamed = (EPI == EPI_LSE) && ep.blk_tiles > 0;
+  const int slab = streamed ? ep.blk_tiles : ((slab_req > 0 && slab_req < num_n) ? slab_req : num_n);
+  const int* slab_order = streamed ? ep.blk_order : nullptr;
 
   if (warp == 0 && elect_one()) {
     prefetch_tmap(&tmA);
@@ -416,7 +450,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&full_bar[i]), 1);
-      mbar_init(smem_u32(&empty_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), CL);      // a slot is rewritten by every CTA of the cluster (B multicast)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
@@ -430,8 +464,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync();            // peers' barriers are initialised before any multicast can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  [[maybe_unused]] const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+  [[maybe_unused]] constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -439,22 +476,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       const int pf_dist = ep.tune & kTunePrefetchMask;
-      const uint64_t ld_policy = (ep.tune & kTuneLoadEvictLast) ? l2_policy_evict_last() : 0;
+      // bit 9: the A operand of the plain GEMMs is the staged dS, read exactly once: mark it evict_first so that the
+      // stream does not push the re-used B operand (the feature matrix) out of L2
+      const uint64_t a_policy = (EPI == EPI_STORE && (ep.tune & kTuneLoadEvictLast)) ? l2_policy_evict_first() : 0;
+      const uint64_t ld_policy = 0;
       // box (64 inner elements x rows) origin of operand X for block index blk and k-block kb
       auto load_a = [&](uint32_t sa, uint32_t fb, int m_blk, int kb) {
         if constexpr (A_MN) {
 #pragma unroll
           for (int u = 0; u < BM / 64; ++u) {
-            if (ld_policy) tma_load_2d_hint(sa + u * (BK * 128), &tmA, fb, m_blk * BM + u * 64, kb * BK, ld_policy);
-            else           tma_load_2d(sa + u * (BK * 128), &tmA, fb, m_blk * BM + u * 64, kb * BK);
+            if (a_policy) tma_load_2d_hint(sa + u * (BK * 128), &tmA, fb, m_blk * BM + u * 64, kb * BK, a_policy);
+            else          tma_load_2d(sa + u * (BK * 128), &tmA, fb, m_blk * BM + u * 64, kb * BK);
           }
         } else {
-          if (ld_policy) tma_load_2d_hint(sa, &tmA, fb, kb * BK, m_blk * BM, ld_policy);
-          else           tma_load_2d(sa, &tmA, fb, kb * BK, m_blk * BM);
+          if (a_policy) tma_load_2d_hint(sa, &tmA, fb, kb * BK, m_blk * BM, a_policy);
+          else          tma_load_2d(sa, &tmA, fb, kb * BK, m_blk * BM);
         }
       };
       auto load_b = [&](uint32_t sb, uint32_t fb, int n_blk, int kb) {
-        if constexpr (B_MN) {
+        if constexpr (CL > 1) {
+          // this CTA's 1/CL slice of the shared B tile, multicast to the whole cluster
+          if constexpr (B_MN) {
+            constexpr int per = BN / 64 / CL;
+#pragma unroll
+            for (int uu = 0; uu < per; ++uu) {
+              const int u = (int)cta_rank * per + uu;
+              tma_load_2d_mc(sb + u * (BK * 128), &tmB, fb, n_blk * BN + u * 64, kb * BK, kClMask);
+            }
+          } else {
+            constexpr int rows = BN / CL;
+            tma_load_2d_mc(sb + cta_rank * (rows * 128), &tmB, fb, kb * BK, n_blk * BN + (int)cta_rank * rows, kClMask);
+          }
+        } else if constexpr (B_MN) {
 #pragma unroll
           for (int u = 0; u < BN / 64; ++u) {
             if (ld_policy) tma_load_2d_hint(sb + u * (BK * 128), &tmB, fb, n_blk * BN + u * 64, kb * BK, ld_policy);
@@ -479,11 +532,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_prefetch_2d(&tmB, kb * BK, n_blk * BN);
         }
       };
+      int slab_seen = -1;
+      const int epoch = (streamed && ep.ready_flags) ? ep.epoch_p[0] : 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int m_blk, n_blk;
-        tile_coords(tile, num_m, num_n, m_blk, n_blk);
+        int m_blk, n_blk, s_idx;
+        tile_coords(tile, num_m, num_n, slab, slab_order, m_blk, n_blk, &s_idx);
+        if (streamed && s_idx != slab_seen) {
+          // first tile of this CTA in a new column block: its rows of the gather buffer must have landed (the copy
+          // engine writes the flag right behind the block); order the TMA (async proxy) reads after the acquire
+          if (ep.ready_flags && ep.blk_wait[s_idx]) {
+            wait_flag_eq(ep.ready_flags + ep.blk_order[s_idx], epoch);
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          slab_seen = s_idx;
+        }
         int m_nxt = -1, n_nxt = -1;
-        if (pf_dist && tile + (int)gridDim.x < num_tiles) tile_coords(tile + gridDim.x, num_m, num_n, m_nxt, n_nxt);
+        if (pf_dist && tile + (int)gridDim.x < num_tiles) tile_coords(tile + gridDim.x, num_m, num_n, slab, slab_order, m_nxt, n_nxt);
         for (int kb = 0; kb < num_k; ++kb) {
           if (pf_dist) {
             // pull the operands pf_dist k-blocks ahead (possibly of this CTA's next tile) into L2 so the smem loads
@@ -534,7 +598,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(d_tmem, da + (uint64_t)k * a_step, db + (uint64_t)k * b_step, idesc, (uint32_t)((kb | k) != 0));
-          umma_commit(smem_u32(&empty_bar[stage]));       // frees the smem slot when the MMAs retire
+          // frees the smem slot when the MMAs retire -- in every CTA of the cluster, whose producers all write it
+          if constexpr (CL > 1) umma_commit_mc(smem_u32(&empty_bar[stage]), kClMask);
+          else                  umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(smem_u32(&tfull_bar[acc]));           // accumulator ready for the epilogue
@@ -554,7 +620,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     [[maybe_unused]] const uint64_t store_policy = (ep.tune & kTuneStoreEvictFirst) ? l2_policy_evict_first() : 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
-      tile_coords(tile, num_m, num_n, m_blk, n_blk);
+      tile_coords(tile, num_m, num_n, slab, slab_order, m_blk, n_blk);
       const int gi = m_blk * BM + q * 32 + lane;          // this thread's row
       const int n_base = n_blk * BN + h * 128;            // first column of this warp's half
       // interior tiles (no ragged edge in this warp's 32 x 128 block) take the branch-free code
@@ -654,6 +720,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync();            // no CTA exits while a peer may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -710,11 +777,9 @@ static int make_store_tmap_bf16(CUtensorMap* tm, void* base, int rows, int cols,
   return XTAG_OK;
 }
 
-template <int EPI, bool A_MN, bool B_MN>
-static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiParams& ep_in,
-                     cudaStream_t st) {
-  EpiParams ep = ep_in;
-  ep.tune = tc_tune();
+template <int EPI, bool A_MN, bool B_MN, int CL>
+static int launch_tc_cl(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiParams& ep,
+                        cudaStream_t st, int grid, int* grid_used) {
   CUtensorMap tmA, tmB, tmC;
   memset(&tmC, 0, sizeof(tmC));
   if (EPI == EPI_DS) {
@@ -723,29 +788,73 @@ static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, in
   }
   int rc = A_MN ? make_tmap_bf16(&tmA, A, K, M, lda, BK) : make_tmap_bf16(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = B_MN ? make_tmap_bf16(&tmB, B, K, N, ldb, BK) : make_tmap_bf16(&tmB, B, N, K, ldb, BN);
+  // K-major B: each CTA of a cluster fetches BN / CL rows of the shared tile
+  rc = B_MN ? make_tmap_bf16(&tmB, B, K, N, ldb, BK) : make_tmap_bf16(&tmB, B, N, K, ldb, BN / CL);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    XTAG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    XTAG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, A_MN, B_MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kSmemBytes));
     attr_set = true;
   }
-  const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  int grid = num_sms();
-  if (grid > num_tiles) grid = num_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  if (CL > 1) {
+    // a persistent kernel needs every cluster co-resident: GPCs with a number of free SMs that is not a multiple of
+    // CL leave SMs unused, so the grid is sized by what the device can actually hold
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      int n = 0;
+      XTAG_CUDA(cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<EPI, A_MN, B_MN, CL>, &cfg));
+      XTAG_REQUIRE(n > 0, XTAG_ERR_CUDA, "no cluster of %d CTAs with %d bytes of shared memory fits on this device", CL,
+                   kSmemBytes);
+      max_clusters = n;
+    }
+    if (grid > max_clusters * CL) grid = max_clusters * CL;
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  }
+  if (grid_used) *grid_used = grid;
   {
     ProfScope prof(EPI, 2.0 * (double)M * (double)N * (double)K, st);
-    tc_gemm_kernel<EPI, A_MN, B_MN><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmC, M, N, K, ep);
+    XTAG_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, A_MN, B_MN, CL>, tmA, tmB, tmC, M, N, K, ep));
   }
   XTAG_CHECK_LAUNCH();
   return XTAG_OK;
 }
 
-int tc_grid_for(int M, int N) {
+// Cluster size for a problem: the CL CTAs of a cluster take CL consecutive tiles of the static schedule, which are CL
+// consecutive m tiles of one n tile exactly when the number of m tiles is a multiple of CL (tile_coords groups m first).
+static int pick_cluster(int M, int N, int tune) {
+  const int want = (tune & kTuneCluster4) ? 4 : (tune & kTuneCluster2) ? 2 : 1;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  int cl = want;
+  while (cl > 1 && (num_m % cl != 0 || (long)num_m * num_n < 2L * cl)) cl >>= 1;
+  return cl;
+}
+
+template <int EPI, bool A_MN, bool B_MN>
+static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiParams& ep_in,
+                     cudaStream_t st, int* grid_used = nullptr) {
+  EpiParams ep = ep_in;
+  ep.tune = tc_tune();
   const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int cl = pick_cluster(M, N, ep.tune);
   int grid = num_sms();
-  return grid > num_tiles ? num_tiles : grid;
+  if (grid > num_tiles) grid = num_tiles;
+  grid -= grid % cl;
+  if (cl == 4) return launch_tc_cl<EPI, A_MN, B_MN, 4>(A, lda, B, ldb, M, N, K, ep, st, grid, grid_used);
+  if (cl == 2) return launch_tc_cl<EPI, A_MN, B_MN, 2>(A, lda, B, ldb, M, N, K, ep, st, grid, grid_used);
+  return launch_tc_cl<EPI, A_MN, B_MN, 1>(A, lda, B, ldb, M, N, K, ep, st, grid, grid_used);
 }
 
 int launch_lse_reduce(const float* parts, int P, int n, float in_mul, float out_mul, float* out, cudaStream_t st);
@@ -796,6 +905,36 @@ int tc_clip_fwd_block(const void* A, const void* Bm, int M, int N, int D, const 
   return launch_tc<EPI_LSE, false, false>(A, D, Bm, D, M, N, D, ep, st);
 }
 
+// Streamed forward: one persistent launch over the whole [N, D] gather buffer whose column blocks (blk_cols rows of Bm
+// each) arrive one after the other; block order[k] is visited k-th and (wait[k]) only after ready_flags[order[k]] ==
+// *epoch.  Same partial layout as tc_clip_fwd: row_part [2*num_n][M], col_part [num_m][col_ld].
+int tc_clip_fwd_stream(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
+                       const int* order, const int* wait, int nblk, int blk_cols, const int* ready_flags,
+                       const int* epoch, float* row_part, float* col_part, int col_ld, float* diag, cudaStream_t st) {
+  XTAG_REQUIRE(nblk >= 1 && nblk <= 16 && blk_cols % BN == 0 && (long)nblk * blk_cols == (long)N, XTAG_ERR_UNSUPPORTED,
+               "clip_fwd_stream: needs <= 16 column blocks of a multiple of %d columns (nblk=%d, blk_cols=%d, N=%d)", BN,
+               nblk, blk_cols, N);
+  EpiParams ep = {};
+  ep.scale_p = scale;
+  ep.label_offset = label_offset;
+  ep.row_part = row_part;
+  ep.col_part = col_part;
+  ep.col_ld = col_ld;
+  ep.diag = diag;
+  ep.ready_flags = ready_flags;
+  ep.epoch_p = epoch;
+  ep.blk_tiles = blk_cols / BN;
+  bool seen[16] = {};
+  for (int k = 0; k < nblk; ++k) {
+    XTAG_REQUIRE(order[k] >= 0 && order[k] < nblk && !seen[order[k]], XTAG_ERR_INVALID,
+                 "clip_fwd_stream: order must be a permutation of the column blocks");
+    seen[order[k]] = true;
+    ep.blk_order[k] = order[k];
+    ep.blk_wait[k] = wait[k] ? 1 : 0;
+  }
+  return launch_tc<EPI_LSE, false, false>(A, D, Bm, D, M, N, D, ep, st);
+}
+
 // Backward workspace: dS [M][Np] bf16 (Np = N padded to 8 so rows stay 16-byte multiples) + d(logit_scale) partials.
 // The two gradient GEMMs read dS and the features in place through MN-major UMMA descriptors.
 struct BwdLayout {
@@ -835,8 +974,8 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
     ep.grad_out = grad_out;
     ep.dS = dS; ep.ldds = (int)L.Np;
     ep.dscale_part = part;
-    const int grid = tc_grid_for(M, N);
-    rc = launch_tc<EPI_DS, false, false>(A, D, Bm, D, M, N, D, ep, st);
+    int grid = 0;
+    rc = launch_tc<EPI_DS, false, false>(A, D, Bm, D, M, N, D, ep, st, &grid);
     if (rc) return rc;
     if (dscale) {
       rc = launch_sum_into(part, grid * kEpiWarps, dscale, st);

@@ -41,7 +41,7 @@ int tc_tune() {
   int t = g_tune.load(std::memory_order_relaxed);
   if (t < 0) {
     const char* e = getenv("XTAG_TC_TUNE");
-    t = e ? (int)strtol(e, nullptr, 0) & 0xffff : kDefaultTune;
+    t = e ? (int)strtol(e, nullptr, 0) & 0xffffff : kDefaultTune;
     g_tune.store(t, std::memory_order_relaxed);
   }
   return t;
@@ -107,7 +107,7 @@ int xtag_prof_read(int* tags, float* ms, double* work, int cap) {
 
 int xtag_set_tune(int bits) {
   const int old = xtag::tc_tune();
-  xtag::g_tune.store(bits & 0xffff, std::memory_order_relaxed);
+  xtag::g_tune.store(bits & 0xffffff, std::memory_order_relaxed);
   return old;
 }
 

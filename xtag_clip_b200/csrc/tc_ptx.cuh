@@ -50,8 +50,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+    if (clock64() - t0 > 60000000000LL) {   // ~30 s at 2 GHz (a streamed forward legitimately waits for slow peers)
       printf("xtag: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+// Spin until the 32-bit word at `p` equals `want` (written by a copy engine or a peer GPU after the data it guards).
+// Bounded (~30 s) like the mbarrier waits.
+__device__ __forceinline__ void wait_flag_eq(const int* p, int want) {
+  int v;
+  asm volatile("ld.acquire.sys.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  if (v == want) return;
+  const long long t0 = clock64();
+  while (true) {
+    __nanosleep(200);
+    asm volatile("ld.acquire.sys.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v == want) return;
+    if (clock64() - t0 > 60000000000LL) {
+      printf("xtag: ready-flag timeout block %d flag %p = %d, expected %d\n", blockIdx.x, p, v, want);
       __trap();
     }
   }
@@ -77,6 +95,24 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst_smem, const CUtens
       "[%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
+}
+// multicast load: the box lands at the same shared-memory offset of every CTA in `cta_mask` (bit i = cluster rank i)
+// and completes `bytes` on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // L2 prefetch of the tile a later tma_load_2d with the same coordinates will fetch (no smem, no barrier)
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
@@ -138,6 +174,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // all previously issued tcgen05.mma of this thread arrive on `bar` when complete
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// same, arriving on the mbarrier at this shared-memory offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives TMEM lane (base_lane + t),

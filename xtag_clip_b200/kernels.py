@@ -149,6 +149,40 @@ class CudaKernels:
               "xtag_lse_reduce_log2")
         return row_lse, col, st["diag"]
 
+    # ---- K1 fused with the exchange: one persistent launch gated by per-block ready flags -----------------------
+    def supports_fwd_stream(self, A: torch.Tensor, blk_cols: int, nblk: int) -> bool:
+        return self.supports_fwd_blocks(A) and blk_cols % 256 == 0 and 1 <= nblk <= 16
+
+    def clip_fwd_stream(self, A: torch.Tensor, Bm_all: torch.Tensor, scale: torch.Tensor, label_offset: int,
+                        order, wait, blk_cols: int, ready_flags: Optional[torch.Tensor],
+                        epoch: Optional[torch.Tensor], col_out: Optional[torch.Tensor] = None):
+        """-> (row_lse [M], col_lse_partial [N] (in col_out when given), diag [M]).  Bm_all [N, D] is the gather buffer;
+        block order[k] (blk_cols rows) is visited k-th, after ready_flags[order[k]] == epoch when wait[k]."""
+        import ctypes
+        _cuda(A, Bm_all, scale, ready_flags, epoch)
+        assert A.is_contiguous() and Bm_all.is_contiguous()
+        M, D = A.shape
+        N = Bm_all.shape[0]
+        nblk = len(order)
+        assert nblk * blk_cols == N and len(wait) == nblk
+        dev = A.device
+        rp, cp = ctypes.c_int(0), ctypes.c_int(0)
+        check(self.lib.xtag_clip_fwd_block_parts(M, N, ctypes.byref(rp), ctypes.byref(cp)), "xtag_clip_fwd_block_parts")
+        row_part = torch.empty((rp.value, M), dtype=torch.float32, device=dev)
+        col_part = torch.empty((cp.value, N), dtype=torch.float32, device=dev)
+        diag = torch.empty(M, dtype=torch.float32, device=dev)
+        row_lse = torch.empty(M, dtype=torch.float32, device=dev)
+        col = col_out if col_out is not None else torch.empty(N, dtype=torch.float32, device=dev)
+        assert col.is_contiguous() and col.numel() == N
+        o_arr = (ctypes.c_int * nblk)(*[int(x) for x in order])
+        w_arr = (ctypes.c_int * nblk)(*[int(bool(x)) for x in wait])
+        check(self.lib.xtag_clip_fwd_stream(_p(A), _p(Bm_all), _dt(A), M, N, D, _p(scale), int(label_offset),
+                                            o_arr, w_arr, nblk, int(blk_cols), _p(ready_flags), _p(epoch),
+                                            _p(row_part), _p(col_part), N, _p(diag), _stream()), "xtag_clip_fwd_stream")
+        check(self.lib.xtag_lse_reduce_log2(_p(row_part), rp.value, M, _p(row_lse), _stream()), "xtag_lse_reduce_log2")
+        check(self.lib.xtag_lse_reduce_log2(_p(col_part), cp.value, N, _p(col), _stream()), "xtag_lse_reduce_log2")
+        return row_lse, col, diag
+
     def lse_combine(self, parts: torch.Tensor) -> torch.Tensor:
         _cuda(parts)
         parts = parts.contiguous()

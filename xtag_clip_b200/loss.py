@@ -160,6 +160,7 @@ class _Cfg:
     comm_dtype: Optional[torch.dtype]
     pipeline: bool = True
     symm: bool = True
+    stream_fwd: bool = True
 
 
 def _as_scale_tensor(logit_scale, device) -> torch.Tensor:
@@ -186,15 +187,27 @@ class _FusedClipLoss(torch.autograd.Function):
             B = b * W
             txt_all = torch.empty((B, txt.shape[1]), dtype=txt.dtype, device=txt.device)
             sx = cfg.comm.symm_exchange(txt) if cfg.symm else None
-            if sx is not None:
+            streamed = (sx is not None and cfg.stream_fwd and hasattr(K, "supports_fwd_stream")
+                        and K.supports_fwd_stream(img, b, W))
+            if streamed:
+                # K1 fused with the exchange: ONE persistent launch consumes the gather buffer block by block, gated by
+                # the ready flags the copy stream writes behind each pulled block
+                sx.begin_step()
+                order, wait = sx.gather_streamed(txt, txt_all)
+                row_lse, _, diag = K.clip_fwd_stream(img, txt_all, scale, off, order, wait, b, sx.flags, sx.epoch,
+                                                     col_out=sx.col_buffer())
+                plan = []
+            elif sx is not None:
                 sx.begin_step()
                 plan = sx.gather_pipelined(txt, txt_all)          # copy-engine pulls from peer memory
                 col_part = sx.col_buffer()
             else:
                 plan = cfg.comm.pipelined_gather(txt, txt_all)    # batched NCCL P2P rounds
                 col_part = torch.empty(B, dtype=torch.float32, device=txt.device)
-            blocks = hasattr(K, "supports_fwd_blocks") and K.supports_fwd_blocks(img)
-            if blocks:
+            blocks = (not streamed) and hasattr(K, "supports_fwd_blocks") and K.supports_fwd_blocks(img)
+            if streamed:
+                pass
+            elif blocks:
                 # one K1 launch per arriving block, the row / column reductions of all blocks once at the end
                 st = K.clip_fwd_blocks_begin(img, [hi - lo for lo, hi, _ in plan], col_out=col_part)
             else:
@@ -210,12 +223,14 @@ class _FusedClipLoss(torch.autograd.Function):
                 else:
                     rp, _, _ = K.clip_fwd(img, txt_all[lo:hi], scale, lab, col_out=col_part[lo:hi], diag_out=diag)
                     row_parts.append(rp)
-            if blocks:
+            if streamed:
+                pass
+            elif blocks:
                 row_lse, _, diag = K.clip_fwd_blocks_end(st)
             else:
                 row_lse = K.lse_combine(torch.stack(row_parts)) if len(row_parts) > 1 else row_parts[0]
             if sx is not None:
-                sx.end_gather()
+                sx.end_gather(streamed)
                 col_lse = sx.combine_cols(K)                      # barrier + one kernel over the W peer buffers
                 ctx.symm = (sx, sx.step)
             else:
@@ -465,6 +480,7 @@ class ClipLoss(nn.Module):
             comm_dtype: Optional[torch.dtype] = None,
             pipeline: bool = True,
             symmetric_memory: bool = True,
+            stream_forward: bool = True,
             cuda_graph: bool = False,
             _kernels=None,
     ):
@@ -482,6 +498,7 @@ class ClipLoss(nn.Module):
         self._comm_dtype = comm_dtype
         self._pipeline = pipeline
         self._symm = symmetric_memory
+        self._stream_fwd = stream_forward
         self._cuda_graph = cuda_graph
         self._graphs = {}
         self._kernels = _kernels
@@ -535,7 +552,7 @@ class ClipLoss(nn.Module):
                 self._comm = _Comm(self.world_size, self.rank, self._group)     # keeps its side stream
             comm = self._comm
         return _Cfg(self.local_loss, self.gather_with_grad, self.rank, self.world_size, k, comm, self._comm_dtype,
-                    self._pipeline, self._symm)
+                    self._pipeline, self._symm, self._stream_fwd)
 
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
         if image_features.dim() != 2 or image_features.shape != text_features.shape:

@@ -67,6 +67,10 @@ class SymmExchange:
         self.s2 = torch.cuda.Stream(device=device)
         self.step = 0
         self.slot = 0
+        # streamed forward: per-block ready flags, written by the copy stream right behind each pulled block with the
+        # step's epoch value (a device counter, so a captured step replays with fresh values)
+        self.flags = torch.zeros(world, dtype=torch.int32, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
 
     # ---- schedule ---------------------------------------------------------------------------------------------
     def _blocks(self) -> List[Tuple[int, int, List[int]]]:
@@ -115,9 +119,31 @@ class SymmExchange:
             plan.append((lo_r * b, hi_r * b, evs))
         return plan
 
-    def end_gather(self):
-        """the pull streams must be drained before the next barrier on s1 (orders the next overwrite of a slot)"""
-        self.s1.wait_stream(self.s2)
+    def gather_streamed(self, x: torch.Tensor, out_all: torch.Tensor):
+        """Pull the peers' blocks one after the other on ONE copy stream (copy-engine transfers of one GPU serialise
+        anyway; a single stream fixes their order) in ring order r+1, r+2, ..., each followed by a 4-byte copy of the
+        step's epoch into its ready flag.  Returns (order, wait) for `clip_fwd_stream`: the persistent K1 launch on the
+        compute stream starts with the rank's own block and picks up each peer block the moment its flag flips -- no
+        event waits, no launch per block.  `end_gather` joins the copy stream afterwards."""
+        b, s, W, r = self.b, self.slot, self.W, self.r
+        cur = torch.cuda.current_stream()
+        self.epoch.add_(1)                                  # compute stream, before the fork: ordered before K1 reads it
+        out_all[r * b:(r + 1) * b].copy_(x)
+        self.s1.wait_stream(cur)
+        order = [(r + j) % W for j in range(W)]
+        with torch.cuda.stream(self.s1):
+            self.feat[s].copy_(x)
+            self.h_feat.barrier(channel=0)                  # every rank's slot s is written
+            for p in order[1:]:
+                out_all[p * b:(p + 1) * b].copy_(self.peer_feat[p][s], non_blocking=True)
+                self.flags[p:p + 1].copy_(self.epoch, non_blocking=True)
+        return order, [False] + [True] * (W - 1)
+
+    def end_gather(self, streamed: bool = False):
+        """the pull streams must be drained before the next barrier on s1 (orders the next overwrite of a slot).
+        The streamed gather never forks s2 (waiting on it would pull an un-captured stream into a graph capture)."""
+        if not streamed:
+            self.s1.wait_stream(self.s2)
         torch.cuda.current_stream().wait_stream(self.s1)
 
     # ---- forward: column-LSE exchange -------------------------------------------------------------------------
