@@ -28,3 +28,10 @@ from .tag_oracle import (  # noqa: F401
     asymmetric_loss,
     control_word_indices,
 )
+from .fusion_oracle import (  # noqa: F401
+    FUSION_CFG,
+    make_fusion_params,
+    fusion_forward,
+    fusion_scores,
+    dqn_cos_loss,
+)

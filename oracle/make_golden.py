@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_shim  # noqa: E402
 from oracle.tag_oracle import make_tag_params  # noqa: E402
+from oracle.fusion_oracle import make_fusion_params  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -201,6 +202,66 @@ def golden_tag_head():
     print("tag_head.npz")
 
 
+def golden_fusion():
+    """TQN fusion head + DQNCOSLoss exactly as CLIP.forward / the training loop chain them (model.py:552-561,
+    train_other.py:130-132): the reference's own TQN_Model (built with a cfg object for the small widths, default
+    construction for 512) with deterministic parameters, both directions, loss and gradients."""
+    ref_shim.load_ref_open_clip()
+    from open_clip.CAR_heads.TQN_model import TQN_Model
+    asl = ref_shim.load_ref_asl()
+    out = {}
+    cases = [  # (seed, d_model, layers, B, image tokens, text tokens)
+        (60, 64, 4, 6, 10, 7),
+        (61, 32, 2, 3, 50, 5),
+        (62, 512, 4, 4, 12, 9),
+    ]
+    for n, (seed, d, layers, B, Pi, Pt) in enumerate(cases):
+        if d == 512 and layers == 4:
+            model = TQN_Model()                                 # the way CLIP.__init__ builds it (model.py:286)
+        else:
+            cfg = types.SimpleNamespace(MODEL=types.SimpleNamespace(FUSION_DIM=d, FUSION_CLASS_NUM=1,
+                                                                    FUSION_DECODER_NUM=layers))
+            model = TQN_Model(cfg)
+        model = model.double().eval()
+        model.load_state_dict(make_fusion_params(seed, d, 1, layers), strict=True)
+        g = torch.Generator().manual_seed(seed + 1000)
+        out_token = torch.randn(B, Pi, d, generator=g, dtype=torch.float32).double().requires_grad_(True)
+        text_tokens = torch.randn(B, Pt, d, generator=g, dtype=torch.float32).double().requires_grad_(True)
+        # model.py:552-561
+        text_features_l, text_features_g = text_tokens.clone(), text_tokens.clone().mean(axis=1)
+        image_features_l, image_features_g = out_token.clone(), out_token.clone().mean(axis=1)
+        i2t = model(torch.cat([image_features_g.unsqueeze(1), image_features_l], dim=1), text_features_g).squeeze(-1)
+        t2i = model(torch.cat([text_features_g.unsqueeze(1), text_features_l], dim=1), image_features_g).squeeze(-1)
+        ce = asl.DQNCOSLoss()
+        l1, l2 = ce(i2t), ce(t2i)
+        (l1 + l2).backward()
+        pre = f"f{n}_"
+        out[pre + "cfg"] = np.asarray([seed, d, layers, B, Pi, Pt], dtype=np.int64)
+        out[pre + "out_token"] = out_token.detach().numpy()
+        out[pre + "text_tokens"] = text_tokens.detach().numpy()
+        out[pre + "i2t"] = i2t.detach().numpy()
+        out[pre + "t2i"] = t2i.detach().numpy()
+        out[pre + "loss_i2t"] = l1.detach().numpy()
+        out[pre + "loss_t2i"] = l2.detach().numpy()
+        out[pre + "d_out_token"] = out_token.grad.numpy()
+        out[pre + "d_text_tokens"] = text_tokens.grad.numpy()
+        out[pre + "d_inproj0"] = model.decoder.layers[0].multihead_attn.in_proj_weight.grad.numpy()[:6, :8].copy()
+        out[pre + "d_mlp9"] = model.mlp_head[9].weight.grad.numpy().copy()
+        out[pre + "state_keys"] = np.asarray(sorted(model.state_dict().keys()))
+    # DQNCOSLoss alone on matrices with a wide dynamic range
+    gx = torch.Generator().manual_seed(63)
+    for n, (B, amp) in enumerate([(5, 1.0), (17, 30.0), (64, 100.0)]):
+        x = (torch.randn(B, B, generator=gx, dtype=torch.float32) * amp).double().requires_grad_(True)
+        l = asl.DQNCOSLoss()(x)
+        l.backward()
+        out[f"ce{n}_x"] = x.detach().numpy()
+        out[f"ce{n}_loss"] = l.detach().numpy()
+        out[f"ce{n}_dx"] = x.grad.numpy()
+    out["n_cases"] = np.asarray(len(cases))
+    np.savez_compressed(os.path.join(OUT, "fusion.npz"), **out)
+    print("fusion.npz")
+
+
 def main():
     assert ref_shim.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
@@ -210,6 +271,7 @@ def main():
     golden_clip_w1()
     golden_clip_dist()
     golden_tag_head()
+    golden_fusion()
     golden_config1()
 
 

@@ -80,6 +80,9 @@ class ModelKernels:
             col = st["col_out"]
         return row, col, st["diag"]
 
+    def lse_reduce_log2(self, parts):
+        return (torch.logsumexp(_f64(parts) * math.log(2.0), 0)).float()
+
     def lse_combine(self, parts):
         return torch.logsumexp(_f64(parts), 0).float()
 
@@ -126,6 +129,7 @@ class ModelKernels:
 
     def xattn_fwd(self, q, k, v, heads, softmax_scale, dropout_p, seed, offset):
         assert dropout_p == 0.0, "the contract model covers eval mode"
+        self.calls.append(("xattn_fwd", tuple(q.shape), tuple(k.shape), heads))
         o, lse = self._attn(_f64(q), _f64(k), _f64(v), heads, softmax_scale)
         return o.to(q.dtype), lse.float()
 

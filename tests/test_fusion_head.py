@@ -1,0 +1,171 @@
+"""TQN fusion head + DQNCOSLoss: the oracle restatement and the drop-in's host logic
+against fixtures the REFERENCE produced (tests/golden/fusion.npz, oracle/make_golden.py:golden_fusion).  On CPU the
+kernels are the contract model (tests/kernel_model.py); the GPU variants at the bottom run the real K4 / LSE kernels and
+are gated behind XTAG_EXPERIMENTAL=1 until they have been validated on a B200."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+import oracle  # noqa: E402
+import xtag_clip_b200 as xt  # noqa: E402
+from kernel_model import ModelKernels  # noqa: E402
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu().numpy() if torch.is_tensor(a) else np.asarray(a, dtype=np.float64)
+    b = b.detach().double().cpu().numpy() if torch.is_tensor(b) else np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def G(golden_dir):
+    return np.load(os.path.join(golden_dir, "fusion.npz"), allow_pickle=False)
+
+
+def _case(G, n):
+    pre = f"f{n}_"
+    seed, d, layers, B, Pi, Pt = (int(v) for v in G[pre + "cfg"])
+    return pre, seed, d, layers
+
+
+def test_oracle_matches_reference_fusion(G):
+    for n in range(int(G["n_cases"])):
+        pre, seed, d, layers = _case(G, n)
+        params = oracle.make_fusion_params(seed, d, 1, layers)
+        assert sorted(params.keys()) == list(G[pre + "state_keys"])         # the reference's state_dict names
+        img = torch.from_numpy(G[pre + "out_token"]).requires_grad_(True)
+        txt = torch.from_numpy(G[pre + "text_tokens"]).requires_grad_(True)
+        i2t = oracle.fusion_scores(img, txt, params, layers)
+        t2i = oracle.fusion_scores(txt, img, params, layers)
+        assert rel_err(i2t, G[pre + "i2t"]) < 1e-11 and rel_err(t2i, G[pre + "t2i"]) < 1e-11
+        l1, l2 = oracle.dqn_cos_loss(i2t), oracle.dqn_cos_loss(t2i)
+        assert abs(float(l1) - float(G[pre + "loss_i2t"])) < 1e-12 and abs(float(l2) - float(G[pre + "loss_t2i"])) < 1e-12
+        (l1 + l2).backward()
+        assert rel_err(img.grad, G[pre + "d_out_token"]) < 1e-10 and rel_err(txt.grad, G[pre + "d_text_tokens"]) < 1e-10
+
+
+def test_oracle_dqn_cos_loss_wide_range(G):
+    for n in range(3):
+        x = torch.from_numpy(G[f"ce{n}_x"]).requires_grad_(True)
+        l = oracle.dqn_cos_loss(x)
+        l.backward()
+        assert abs(float(l) - float(G[f"ce{n}_loss"])) <= 1e-12 * max(1.0, abs(float(l)))
+        assert rel_err(x.grad, G[f"ce{n}_dx"]) < 1e-12
+
+
+def _head(seed, d, layers, kernels, dtype=torch.float64, device="cpu"):
+    head = xt.FusionHead(d, 1, layers, _kernels=kernels)
+    sd = oracle.make_fusion_params(seed, d, 1, layers)
+    head.load_state_dict(sd, strict=True)                                   # reference key names, incl. the inert ones
+    return head.to(device=device, dtype=dtype).eval()
+
+
+def test_fusion_head_host_logic_matches_reference(G):
+    """FusionHead / fusion_scores / DQNCOSLoss with the contract-model kernels: values, token gradients and two
+    weight-gradient slices equal what the reference's TQN_Model + DQNCOSLoss produced."""
+    for n in range(int(G["n_cases"])):
+        pre, seed, d, layers = _case(G, n)
+        K = ModelKernels()
+        head = _head(seed, d, layers, K)
+        assert sorted(head.state_dict().keys()) == list(G[pre + "state_keys"])
+        img = torch.from_numpy(G[pre + "out_token"]).requires_grad_(True)
+        txt = torch.from_numpy(G[pre + "text_tokens"]).requires_grad_(True)
+        i2t = xt.fusion_scores(head, img, txt)
+        t2i = xt.fusion_scores(head, txt, img)
+        assert rel_err(i2t, G[pre + "i2t"]) < 1e-9 and rel_err(t2i, G[pre + "t2i"]) < 1e-9
+        ce = xt.DQNCOSLoss(_kernels=K)
+        l1, l2 = ce(i2t), ce(t2i)
+        assert abs(float(l1) - float(G[pre + "loss_i2t"])) < 1e-6 and abs(float(l2) - float(G[pre + "loss_t2i"])) < 1e-6
+        (l1 + l2).backward()
+        assert rel_err(img.grad, G[pre + "d_out_token"]) < 1e-5 and rel_err(txt.grad, G[pre + "d_text_tokens"]) < 1e-5
+        gi = head.decoder.layers[0].multihead_attn.in_proj_weight.grad[:6, :8]
+        assert rel_err(gi, G[pre + "d_inproj0"]) < 1e-5
+        assert rel_err(head.mlp_head[9].weight.grad, G[pre + "d_mlp9"]) < 1e-5
+
+
+def test_fusion_head_query_chunks_and_seq_first_queries():
+    """More queries than one K4 launch holds (chunks of 64 share K/V), and the `inside_repeat=False` calling form."""
+    K = ModelKernels()
+    d, layers, B, P, Q = 32, 2, 3, 11, 150
+    head = _head(5, d, layers, K)
+    params = oracle.make_fusion_params(5, d, 1, layers)
+    g = torch.Generator().manual_seed(3)
+    mem = torch.randn(B, P, d, generator=g, dtype=torch.float64)
+    qf = torch.randn(Q, d, generator=g, dtype=torch.float64)
+    out = head(mem, qf)
+    assert out.shape == (B, Q, 1)
+    assert rel_err(out, oracle.fusion_forward(mem, qf, params, layers)) < 1e-9
+    assert sum(1 for c in K.calls if c[0] == "xattn_fwd") == layers * 3     # ceil(150 / 64) launches per layer
+    out2 = head(mem, qf.unsqueeze(1).repeat(1, B, 1), inside_repeat=False)
+    assert rel_err(out2, out) < 1e-12
+    with pytest.raises(NotImplementedError):
+        head(mem, qf, return_atten=True)
+    with pytest.raises(ValueError):
+        head(mem[..., :16], qf)
+    with pytest.raises(ValueError):
+        xt.DQNCOSLoss(_kernels=K)(torch.zeros(3, 4))
+
+
+def test_dqn_cos_loss_drop_in_matches_reference(G):
+    K = ModelKernels()
+    for n in range(3):
+        x = torch.from_numpy(G[f"ce{n}_x"]).float().requires_grad_(True)
+        l = xt.DQNCOSLoss(_kernels=K)(x)
+        l.backward()
+        # fp32 LSEs of logits up to |x| ~ 400: the exponent rounding (eps * |x|) is the error of the probabilities
+        assert abs(float(l) - float(G[f"ce{n}_loss"])) <= 2e-6 * max(1.0, abs(float(G[f"ce{n}_loss"])))
+        assert rel_err(x.grad, G[f"ce{n}_dx"]) < 5e-5
+
+
+def test_from_reference_live():
+    """Against the reference tree itself when it is present (build container only)."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    ref_shim.load_ref_open_clip()
+    from open_clip.CAR_heads.TQN_model import TQN_Model
+    torch.manual_seed(0)
+    ref = TQN_Model().double().eval()
+    head = xt.FusionHead.from_reference(ref, _kernels=ModelKernels()).eval()
+    g = torch.Generator().manual_seed(9)
+    mem = torch.randn(2, 8, 512, generator=g, dtype=torch.float64)
+    qf = torch.randn(2, 512, generator=g, dtype=torch.float64)
+    assert rel_err(head(mem, qf), ref(mem, qf)) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ GPU (gated)
+gpu_experimental = pytest.mark.skipif(os.environ.get("XTAG_EXPERIMENTAL") != "1",
+                                      reason="fusion head on the GPU: not yet validated on a B200 (set XTAG_EXPERIMENTAL=1)")
+
+
+@pytest.mark.gpu
+@gpu_experimental
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+def test_fusion_head_gpu(G, dtype, tol):
+    pre, seed, d, layers = _case(G, 2)                                      # d_model 512: head dim 128 (tensor-core K4)
+    head = _head(seed, d, layers, None, dtype=dtype, device="cuda")
+    img = torch.from_numpy(G[pre + "out_token"]).to("cuda", dtype).requires_grad_(True)
+    txt = torch.from_numpy(G[pre + "text_tokens"]).to("cuda", dtype).requires_grad_(True)
+    i2t = xt.fusion_scores(head, img, txt)
+    assert rel_err(i2t.float(), G[pre + "i2t"]) < tol
+    loss = xt.DQNCOSLoss()(i2t.float())
+    assert abs(float(loss) - float(G[pre + "loss_i2t"])) < tol
+    loss.backward()
+    assert torch.isfinite(img.grad.float()).all() and torch.isfinite(txt.grad.float()).all()
+
+
+@pytest.mark.gpu
+@gpu_experimental
+def test_dqn_cos_loss_gpu(G):
+    for n in range(3):
+        x = torch.from_numpy(G[f"ce{n}_x"]).float().cuda().requires_grad_(True)
+        l = xt.DQNCOSLoss()(x)
+        l.backward()
+        assert abs(float(l) - float(G[f"ce{n}_loss"])) <= 1e-5 * max(1.0, abs(float(G[f"ce{n}_loss"])))
+        assert rel_err(x.grad, G[f"ce{n}_dx"]) < 1e-4

@@ -183,6 +183,16 @@ class CudaKernels:
         check(self.lib.xtag_lse_reduce_log2(_p(col_part), cp.value, N, _p(col), _stream()), "xtag_lse_reduce_log2")
         return row_lse, col, diag
 
+    def lse_reduce_log2(self, parts: torch.Tensor) -> torch.Tensor:
+        """parts [P, n] fp32 in the log2 domain -> out[j] = ln sum_p 2^parts[p, j]  (natural log)"""
+        _cuda(parts)
+        assert parts.dim() == 2 and parts.dtype == torch.float32
+        parts = parts.contiguous()
+        P, n = parts.shape
+        out = torch.empty(n, dtype=torch.float32, device=parts.device)
+        check(self.lib.xtag_lse_reduce_log2(_p(parts), P, n, _p(out), _stream()), "xtag_lse_reduce_log2")
+        return out
+
     def lse_combine(self, parts: torch.Tensor) -> torch.Tensor:
         _cuda(parts)
         parts = parts.contiguous()
