@@ -53,13 +53,18 @@ uint64_t    xtag_launch_count(void);
 /* Diagnostics for bench.py's roofline: while enabled, every tcgen05 launch is bracketed by CUDA events on
  * its stream.  xtag_prof_read synchronises them and returns up to `cap` records: tag (0 = K1 forward,
  * 1 = K2 dS producer, 2 = plain GEMM), duration in ms, algorithmic FLOPs (2*M*N*K).  enable(0/1) clears. */
-/* Runtime tuning bits of the tcgen05 kernels (no reference counterpart; diagnostics / A-B measurements):
- *   bits [0,8)  L2 prefetch distance of the TMA producer in 64-wide k-blocks (0 = off)
- *   bit 8       dS tile stores carry an L2 evict_first policy      bit 9   operand loads carry evict_last
- *   bit 10      force the two-exponential dS epilogue (default: one exponential per element when the block's
- *               row/column log-sum-exps are within 2^60 of each other, exact two-exp path otherwise)
- *   bit 11      K4 backward as ONE single-pass kernel (K and V streamed once, dK/dV by TMA tile stores) instead of
- *               the query-major dQ kernel + key-major dK/dV kernel pair
+/* Runtime tuning bits of the kernels (no reference counterpart; A/B measurements and diagnostics -- DESIGN.md
+ * section 4 lists what each measured on B200):
+ *   bits [0,8)   L2 prefetch distance of the TMA producer in 64-wide k-blocks (0 = off)
+ *   bit 8        dS tile stores carry an L2 evict_first policy
+ *   bit 9        the streamed A operand (staged dS) of the gradient GEMMs is loaded evict_first
+ *   bit 10       force the two-exponential dS epilogue (default: one exponential per element when the block's
+ *                row/column log-sum-exps are within 2^60 of each other, exact two-exp path otherwise)
+ *   bit 11       K4 backward as ONE single-pass kernel (K and V streamed once, dK/dV by TMA tile stores) instead of
+ *                the query-major dQ kernel + key-major dK/dV kernel pair                     [default: set]
+ *   bits 12, 13  DIAGNOSTICS, wrong results: skip the dS staging + store / skip only the dS TMA store
+ *   bits 14, 15  thread-block clusters of 2 / 4 CTAs along M, the shared B tile TMA-multicast to the cluster
+ *   bits [16,24) n-slab width (in 256-column tiles) of the tile schedule (0 = one slab)
  * Initial value: environment variable XTAG_TC_TUNE (0x800 if unset).  set returns the previous value. */
 int         xtag_set_tune(int bits);
 int         xtag_get_tune(void);

@@ -74,12 +74,10 @@ struct EpiParams {
   int blk_tiles;          // n tiles per column block (0: not streamed)
   int blk_order[16];      // slab s of the schedule works on column block blk_order[s]
   int blk_wait[16];       // 1: slab s must wait for its ready flag
-  // all epilogues: runtime tuning bits (xtag_set_tune): [0,8) L2 prefetch distance in k-blocks (0 = off),
-  // bit 8 dS tile stores carry an L2 evict_first hint, bit 9 operand loads carry an L2 evict_last hint,
-  // bit 10 forces the two-exponential dS path
+  // all epilogues: runtime tuning bits (xtag_set_tune, documented in include/xtag_b200.h)
   int tune;
 };
-constexpr int kTunePrefetchMask = 0xff, kTuneStoreEvictFirst = 0x100, kTuneLoadEvictLast = 0x200,
+constexpr int kTunePrefetchMask = 0xff, kTuneStoreEvictFirst = 0x100, kTuneStreamAEvictFirst = 0x200,
               kTuneDsTwoExp = 0x400,
               kTuneCluster2 = 0x4000,       // clusters of 2 CTAs along M with TMA multicast of the shared B tile
               kTuneCluster4 = 0x8000,       // clusters of 4
@@ -478,8 +476,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int pf_dist = ep.tune & kTunePrefetchMask;
       // bit 9: the A operand of the plain GEMMs is the staged dS, read exactly once: mark it evict_first so that the
       // stream does not push the re-used B operand (the feature matrix) out of L2
-      const uint64_t a_policy = (EPI == EPI_STORE && (ep.tune & kTuneLoadEvictLast)) ? l2_policy_evict_first() : 0;
-      const uint64_t ld_policy = 0;
+      const uint64_t a_policy = (EPI == EPI_STORE && (ep.tune & kTuneStreamAEvictFirst)) ? l2_policy_evict_first() : 0;
       // box (64 inner elements x rows) origin of operand X for block index blk and k-block kb
       auto load_a = [&](uint32_t sa, uint32_t fb, int m_blk, int kb) {
         if constexpr (A_MN) {
@@ -509,13 +506,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else if constexpr (B_MN) {
 #pragma unroll
-          for (int u = 0; u < BN / 64; ++u) {
-            if (ld_policy) tma_load_2d_hint(sb + u * (BK * 128), &tmB, fb, n_blk * BN + u * 64, kb * BK, ld_policy);
-            else           tma_load_2d(sb + u * (BK * 128), &tmB, fb, n_blk * BN + u * 64, kb * BK);
-          }
+          for (int u = 0; u < BN / 64; ++u) tma_load_2d(sb + u * (BK * 128), &tmB, fb, n_blk * BN + u * 64, kb * BK);
         } else {
-          if (ld_policy) tma_load_2d_hint(sb, &tmB, fb, kb * BK, n_blk * BN, ld_policy);
-          else           tma_load_2d(sb, &tmB, fb, kb * BK, n_blk * BN);
+          tma_load_2d(sb, &tmB, fb, kb * BK, n_blk * BN);
         }
       };
       auto prefetch = [&](int m_blk, int n_blk, int kb) {
