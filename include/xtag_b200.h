@@ -55,7 +55,8 @@ uint64_t    xtag_launch_count(void);
  * 1 = K2 dS producer, 2 = plain GEMM), duration in ms, algorithmic FLOPs (2*M*N*K).  enable(0/1) clears. */
 /* Runtime tuning bits of the kernels (no reference counterpart; A/B measurements and diagnostics -- DESIGN.md
  * section 4 lists what each measured on B200):
- *   bits [0,8)   L2 prefetch distance of the TMA producer in 64-wide k-blocks (0 = off)
+ *   bits [0,8)   L2 prefetch distance of the TMA producer in 64-wide k-blocks (0 = off; 0xff = de-duplicated
+ *                next-tile prefetch: one CTA per shared operand tile asks L2 a whole tile ahead -- not yet measured)
  *   bit 8        dS tile stores carry an L2 evict_first policy
  *   bit 9        the streamed A operand (staged dS) of the gradient GEMMs is loaded evict_first
  *   bit 10       force the two-exponential dS epilogue (default: one exponential per element when the block's

@@ -161,6 +161,7 @@ class _Cfg:
     pipeline: bool = True
     symm: bool = True
     stream_fwd: bool = True
+    pull_streams: int = 1
 
 
 def _as_scale_tensor(logit_scale, device) -> torch.Tensor:
@@ -193,7 +194,7 @@ class _FusedClipLoss(torch.autograd.Function):
                 # K1 fused with the exchange: ONE persistent launch consumes the gather buffer block by block, gated by
                 # the ready flags the copy stream writes behind each pulled block
                 sx.begin_step()
-                order, wait = sx.gather_streamed(txt, txt_all)
+                order, wait = sx.gather_streamed(txt, txt_all, cfg.pull_streams)
                 row_lse, _, diag = K.clip_fwd_stream(img, txt_all, scale, off, order, wait, b, sx.flags, sx.epoch,
                                                      col_out=sx.col_buffer())
                 plan = []
@@ -481,6 +482,7 @@ class ClipLoss(nn.Module):
             pipeline: bool = True,
             symmetric_memory: bool = True,
             stream_forward: bool = True,
+            pull_streams: int = 1,
             cuda_graph: bool = False,
             _kernels=None,
     ):
@@ -499,6 +501,7 @@ class ClipLoss(nn.Module):
         self._pipeline = pipeline
         self._symm = symmetric_memory
         self._stream_fwd = stream_forward
+        self._pull_streams = pull_streams
         self._cuda_graph = cuda_graph
         self._graphs = {}
         self._kernels = _kernels
@@ -552,7 +555,7 @@ class ClipLoss(nn.Module):
                 self._comm = _Comm(self.world_size, self.rank, self._group)     # keeps its side stream
             comm = self._comm
         return _Cfg(self.local_loss, self.gather_with_grad, self.rank, self.world_size, k, comm, self._comm_dtype,
-                    self._pipeline, self._symm, self._stream_fwd)
+                    self._pipeline, self._symm, self._stream_fwd, self._pull_streams)
 
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
         if image_features.dim() != 2 or image_features.shape != text_features.shape:
