@@ -22,5 +22,10 @@ if [ "$N" -ge 2 ]; then
     run nx_bench_n${N}_ps$PS 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
       --master-port 2958$PS bench.py --gpus $N --steps 20 --warmup 5 --pull-streams $PS
   done
+  # push exchange (no start-of-step barrier): parity first, then the bench line
+  XTAG_EXCHANGE=push run nx_dist_push 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+    --master-port 29591 tests/dist_gpu_worker.py
+  XTAG_EXCHANGE=push run nx_bench_n${N}_push 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
+    --master-addr 127.0.0.1 --master-port 29592 bench.py --gpus $N --steps 20 --warmup 5
 fi
 cat $S

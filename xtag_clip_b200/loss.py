@@ -162,6 +162,7 @@ class _Cfg:
     symm: bool = True
     stream_fwd: bool = True
     pull_streams: int = 1
+    exchange: str = "pull"
 
 
 def _as_scale_tensor(logit_scale, device) -> torch.Tensor:
@@ -192,10 +193,14 @@ class _FusedClipLoss(torch.autograd.Function):
                         and K.supports_fwd_stream(img, b, W))
             if streamed:
                 # K1 fused with the exchange: ONE persistent launch consumes the gather buffer block by block, gated by
-                # the ready flags the copy stream writes behind each pulled block
+                # the ready flags the copy stream writes behind each block
                 sx.begin_step()
-                order, wait = sx.gather_streamed(txt, txt_all, cfg.pull_streams)
-                row_lse, _, diag = K.clip_fwd_stream(img, txt_all, scale, off, order, wait, b, sx.flags, sx.epoch,
+                if cfg.exchange == "push":
+                    txt_all, order, wait, flags = sx.gather_pushed(txt)
+                else:
+                    order, wait = sx.gather_streamed(txt, txt_all, cfg.pull_streams)
+                    flags = sx.flags
+                row_lse, _, diag = K.clip_fwd_stream(img, txt_all, scale, off, order, wait, b, flags, sx.epoch,
                                                      col_out=sx.col_buffer())
                 plan = []
             elif sx is not None:
@@ -483,6 +488,7 @@ class ClipLoss(nn.Module):
             symmetric_memory: bool = True,
             stream_forward: bool = True,
             pull_streams: int = 1,
+            exchange: Optional[str] = None,
             cuda_graph: bool = False,
             _kernels=None,
     ):
@@ -502,6 +508,11 @@ class ClipLoss(nn.Module):
         self._symm = symmetric_memory
         self._stream_fwd = stream_forward
         self._pull_streams = pull_streams
+        # "pull" (validated) or "push" (experimental: no start-of-step barrier); default from XTAG_EXCHANGE
+        import os as _os
+        self._exchange = exchange or _os.environ.get("XTAG_EXCHANGE", "pull")
+        if self._exchange not in ("pull", "push"):
+            raise ValueError(f"exchange must be 'pull' or 'push', got {self._exchange!r}")
         self._cuda_graph = cuda_graph
         self._graphs = {}
         self._kernels = _kernels
@@ -555,7 +566,7 @@ class ClipLoss(nn.Module):
                 self._comm = _Comm(self.world_size, self.rank, self._group)     # keeps its side stream
             comm = self._comm
         return _Cfg(self.local_loss, self.gather_with_grad, self.rank, self.world_size, k, comm, self._comm_dtype,
-                    self._pipeline, self._symm, self._stream_fwd, self._pull_streams)
+                    self._pipeline, self._symm, self._stream_fwd, self._pull_streams, self._exchange)
 
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
         if image_features.dim() != 2 or image_features.shape != text_features.shape:

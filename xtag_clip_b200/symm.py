@@ -45,6 +45,7 @@ class SymmExchange:
         self.B = world * b
         self.feat_dtype, self.grad_dtype = feat_dtype, grad_dtype
         grp = group if group is not None else dist.group.WORLD
+        self._grp = grp
         self.feat = symm_mem.empty((2, b, D), dtype=feat_dtype, device=device)
         self.h_feat = symm_mem.rendezvous(self.feat, grp)
         self.col = symm_mem.empty((2, self.B), dtype=torch.float32, device=device)
@@ -150,6 +151,48 @@ class SymmExchange:
                 self.flags[p:p + 1].copy_(self.epoch, non_blocking=True)
         self._streamed_two = len(streams) == 2
         return order, [False] + [True] * (W - 1)
+
+    # ---- forward: PUSH variant of the streamed gather (experimental, not yet validated on hardware) -------------
+    def _push_buffers(self):
+        """Peer-writable gather buffers [2][B, D] and per-slot ready flags [2][W] (lazily: only the push exchange
+        needs them)."""
+        if getattr(self, "gbuf", None) is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = self._grp
+            dev = self.feat.device
+            self.gbuf = symm_mem.empty((2, self.B, self.D), dtype=self.feat_dtype, device=dev)
+            self.h_gbuf = symm_mem.rendezvous(self.gbuf, grp)
+            self.pflags = symm_mem.empty((2, self.W), dtype=torch.int32, device=dev)
+            self.pflags.zero_()
+            self.h_pflags = symm_mem.rendezvous(self.pflags, grp)
+            self.peer_gbuf = [self.h_gbuf.get_buffer(p, (2, self.B, self.D), self.feat_dtype) for p in range(self.W)]
+            self.peer_pflags = [self.h_pflags.get_buffer(p, (2, self.W), torch.int32) for p in range(self.W)]
+            self.h_pflags.barrier(channel=0)                # every rank's flags are zeroed before anyone pushes
+        return self.gbuf, self.pflags
+
+    def gather_pushed(self, x: torch.Tensor):
+        """Every rank PUSHES its block into all peers' gather buffers (copy-engine writes over NVLink, ring order
+        r+1, r+2, ...) and writes the step's epoch into the peer's ready flag behind it.  The consumer is the
+        flag-gated persistent K1 launch, so no barrier is needed before the exchange: a rank that is late only delays
+        its own block at its peers (the pull exchange pays the start-of-step barrier skew, measured 68 us at 8 GPUs).
+        Buffers are double-buffered by step parity; a rank can only be two steps ahead of a peer after passing the
+        previous step's column-LSE barrier, by which time that peer has finished reading the slot.
+        Returns (gather buffer [B, D] of this step, order, wait, flags [W])."""
+        gbuf, pflags = self._push_buffers()
+        b, s, W, r = self.b, self.slot, self.W, self.r
+        cur = torch.cuda.current_stream()
+        self.epoch.add_(1)
+        gbuf[s][r * b:(r + 1) * b].copy_(x)
+        self.s1.wait_stream(cur)
+        with torch.cuda.stream(self.s1):
+            for j in range(1, W):
+                p = (r + j) % W
+                self.peer_gbuf[p][s][r * b:(r + 1) * b].copy_(x, non_blocking=True)
+                self.peer_pflags[p][s][r:r + 1].copy_(self.epoch, non_blocking=True)
+        self._streamed_two = False
+        # the block of rank q is q's ((r - q) % W)-th push: r-1 lands first, then r-2, ...
+        order = [(r - j) % W for j in range(W)]
+        return gbuf[s], order, [False] + [True] * (W - 1), pflags[s]
 
     def end_gather(self, streamed: bool = False):
         """the pull streams must be drained before the next barrier on s1 (orders the next overwrite of a slot).
