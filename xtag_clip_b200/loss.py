@@ -318,6 +318,8 @@ class _FusedClipLoss(torch.autograd.Function):
                     d_img = d_img.to(fdt)
                 if need_t:
                     d_txt = cfg.comm.reduce_scatter_sum(d_txt_all).to(fdt)
+            if ctx.symm is not None and getattr(ctx.symm[0], "_pushed", False):
+                ctx.symm[0].push_step_done()
         elif cfg.local_loss:
             ds = torch.zeros((), dtype=torch.float32, device=img.device)
             if need_i or need_s:

@@ -190,9 +190,17 @@ class SymmExchange:
                 self.peer_gbuf[p][s][r * b:(r + 1) * b].copy_(x, non_blocking=True)
                 self.peer_pflags[p][s][r:r + 1].copy_(self.epoch, non_blocking=True)
         self._streamed_two = False
+        self._pushed = True
         # the block of rank q is q's ((r - q) % W)-th push: r-1 lands first, then r-2, ...
         order = [(r - j) % W for j in range(W)]
         return gbuf[s], order, [False] + [True] * (W - 1), pflags[s]
+
+    def push_step_done(self):
+        """End of a backward in push mode: no rank may start pushing the next step's blocks into a peer's gather buffer
+        while that peer's gradient GEMMs still read it.  Eager steps alternate between two slots and would be safe
+        without this, but a captured step replays ONE slot; the barrier sits right behind the reduce-scatter barrier
+        of the same backward, so the ranks arrive within a few microseconds of each other."""
+        self.h_gbuf.barrier(channel=1)
 
     def end_gather(self, streamed: bool = False):
         """the pull streams must be drained before the next barrier on s1 (orders the next overwrite of a slot).
