@@ -17,6 +17,7 @@ XTAG_EXPERIMENTAL=1 run nx_fusion 300 python -m pytest tests/test_fusion_head.py
 # de-duplicated next-tile L2 prefetch (0x8ff) and the n-slab schedule against the default, sustained state
 run nx_sweep 300 python scripts/tune_sweep.py --tunes 0x800,0x8ff,0x1008ff,0x2008ff,0x100800 --iters 4 --rounds 10
 run nx_all 900 python -m pytest tests -q -m gpu --timeout 600
+run nx_sweep_cfg 600 python scripts/sweep.py
 if [ "$N" -ge 2 ]; then
   for PS in 1 2; do
     run nx_bench_n${N}_ps$PS 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \

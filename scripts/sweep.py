@@ -90,6 +90,43 @@ def main():
         rec = dict(kind="xattn_bwd_bf16", b=b, N=N, ms=t, gbs=b * (4 * 44 + 4 * N) * 1536 / (t * 1e-3) / 1e9)
         print(json.dumps(rec), flush=True)
         out.append(rec)
+    # whole tag head (config 3 shape): fused K4 attention core vs the reference's eager attention (bert.py:219-274:
+    # two batched GEMMs + softmax + dropout + permute copies) with the same weights, fwd + bwd, bf16 autocast
+    import torch.nn.functional as F
+    from xtag_clip_b200 import tag_head as th
+
+    def eager_attention(q, k, v, heads, dropout_p=0.0, seed=0, offset=0, *, _kernels=None):
+        b, Lq, H = q.shape
+        dh = H // heads
+        qh = q.reshape(b, Lq, heads, dh).permute(0, 2, 1, 3)
+        kh = k.reshape(b, -1, heads, dh).permute(0, 2, 1, 3)
+        vh = v.reshape(b, -1, heads, dh).permute(0, 2, 1, 3)
+        p = torch.softmax((qh @ kh.transpose(-1, -2)) / math.sqrt(dh), dim=-1)
+        p = F.dropout(p, dropout_p, dropout_p > 0)
+        return (p @ vh).permute(0, 2, 1, 3).reshape(b, Lq, H)
+
+    for b, N, D in [(1024, 197, 512), (1024, 50, 512), (256, 257, 1024)]:
+        head = xt.TagHead(D).cuda().train()
+        tok = torch.randn(b, N, D, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+
+        def step_head():
+            tok.grad = None
+            head.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = head.tag_forward(tok)
+            out.float().sum().backward()
+
+        t_fused = timeit(step_head, iters=10)
+        orig = th.cross_attention
+        th.cross_attention = eager_attention
+        try:
+            t_eager = timeit(step_head, iters=10)
+        finally:
+            th.cross_attention = orig
+        rec = dict(kind="tag_head_fwd_bwd_train", b=b, N=N, D=D, fused_ms=t_fused, eager_attention_ms=t_eager,
+                   speedup=t_eager / t_fused)
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/sweep.jsonl", "w") as fh:
         for r in out:
