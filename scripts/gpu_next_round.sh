@@ -13,7 +13,7 @@ run() { local name=$1; shift; local to=$1; shift
 python -c "from xtag_clip_b200._cuda_probe import wait_for_cuda; print('cuda', wait_for_cuda())"
 N=$(nvidia-smi -L | wc -l)
 # gated tests of the fusion head / DQNCOSLoss on the real kernels
-XTAG_EXPERIMENTAL=1 run nx_fusion 300 python -m pytest tests/test_fusion_head.py -q -m gpu --timeout 200
+XTAG_EXPERIMENTAL=1 run nx_fusion 300 python -m pytest tests/test_fusion_head.py tests/test_gpu_api.py -q -m gpu --timeout 200 -k "fusion or dqn or chunks"
 # de-duplicated next-tile L2 prefetch (0x8ff) and the n-slab schedule against the default, sustained state
 run nx_sweep 300 python scripts/tune_sweep.py --tunes 0x800,0x8ff,0x1008ff,0x2008ff,0x100800 --iters 4 --rounds 10
 run nx_all 900 python -m pytest tests -q -m gpu --timeout 600

@@ -247,3 +247,28 @@ def test_config1_heads_on_reference_encoder_outputs(golden_dir):
     ref = oracle.clip_loss_closed_form(I2.detach().double().cpu(), T2.detach().double().cpu(),
                                        torch.tensor(float(g["logit_scale"]), dtype=torch.float64))
     assert rel_err(l2, ref[0]) < 1e-3 and rel_err(I2.grad, ref[1]) < 2e-2 and rel_err(T2.grad, ref[2]) < 2e-2
+
+
+@pytest.mark.skipif(os.environ.get("XTAG_EXPERIMENTAL") != "1",
+                    reason="forward_chunks on the GPU: not yet validated on a B200 (set XTAG_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_forward_chunks_gradient_accumulation_gpu(dtype, tol):
+    """train_other.py:140-197 on the real kernels: cached no-grad chunks + one live chunk against the oracle."""
+    g = torch.Generator().manual_seed(8)
+    sizes, D = [256, 128, 384], 256
+    nrm = torch.nn.functional.normalize
+    imgs = [nrm(torch.randn(b, D, generator=g), dim=-1).to(dtype) for b in sizes]
+    txts = [nrm(0.3 * i.float() + 0.7 * torch.randn(i.shape[0], D, generator=g), dim=-1).to(dtype) for i in imgs]
+    live = 1
+    ic = [t.cuda().requires_grad_(j == live) for j, t in enumerate(imgs)]
+    tc = [t.cuda().requires_grad_(j == live) for j, t in enumerate(txts)]
+    s = torch.tensor(14.285714, device="cuda", requires_grad=True)
+    loss = xt.ClipLoss().forward_chunks(ic, tc, s)
+    loss.backward()
+    I = torch.cat(imgs).double()
+    T = torch.cat(txts).double()
+    lo, dI, dT, ds, _, _ = oracle.clip_loss_closed_form(I, T, torch.tensor(14.285714, dtype=torch.float64))
+    a, b = sum(sizes[:live]), sum(sizes[:live + 1])
+    assert rel_err(loss, lo) < (1e-5 if dtype == torch.float32 else 1e-3)
+    assert rel_err(ic[live].grad, dI[a:b]) < tol and rel_err(tc[live].grad, dT[a:b]) < tol
+    assert abs(float(s.grad) - float(ds)) <= 1e-3 * abs(float(ds)) + 2e-5

@@ -91,6 +91,47 @@ def test_cliploss_misc_behaviour():
         xt.ClipLoss()(I, T, 7.5)          # product path on CPU tensors must fail loudly
 
 
+def test_forward_chunks_gradient_accumulation_path():
+    """train_other.py:140-197: cached no-grad features + one live chunk.  forward_chunks equals the reference's
+    cat-then-loss (loss, live-chunk gradients, d logit_scale) while skipping gradient work for the cached chunks."""
+    g = torch.Generator().manual_seed(4)
+    sizes, D = [5, 3, 4], 12
+    imgs = [torch.nn.functional.normalize(torch.randn(b, D, generator=g, dtype=torch.float64), dim=-1) for b in sizes]
+    txts = [torch.nn.functional.normalize(torch.randn(b, D, generator=g, dtype=torch.float64), dim=-1) for b in sizes]
+    for live in range(3):
+        k = ModelKernels()
+        ic = [t.clone().requires_grad_(j == live) for j, t in enumerate(imgs)]
+        tc = [t.clone().requires_grad_(j == live) for j, t in enumerate(txts)]
+        s = torch.tensor(11.0, dtype=torch.float64, requires_grad=True)
+        loss = xt.ClipLoss(_kernels=k).forward_chunks(ic, tc, s)
+        loss.backward()
+        # reference semantics: autograd through the concatenation
+        ir = [t.clone().requires_grad_(j == live) for j, t in enumerate(imgs)]
+        tr = [t.clone().requires_grad_(j == live) for j, t in enumerate(txts)]
+        sr = torch.tensor(11.0, dtype=torch.float64, requires_grad=True)
+        lr = oracle.clip_loss_single(torch.cat(ir), torch.cat(tr), sr)
+        lr.backward()
+        assert rel_err(loss.item(), lr.item()) < 1e-6
+        assert rel_err(ic[live].grad.numpy(), ir[live].grad.numpy()) < 1e-5
+        assert rel_err(tc[live].grad.numpy(), tr[live].grad.numpy()) < 1e-5
+        assert abs(s.grad.item() - sr.grad.item()) < 1e-5 * abs(sr.grad.item()) + 1e-7
+        assert all(t.grad is None for j, t in enumerate(ic) if j != live)
+        # gradient work only for the live blocks: one dS-only pass (logit_scale) + two rectangular calls
+        bwd = [c for c in k.calls if c[0] == "clip_bwd"]
+        lo = sum(sizes[:live])
+        assert [c[1][0] for c in bwd] == [sum(sizes), sizes[live], sizes[live]] and all(c[3] in (0, lo) for c in bwd)
+    # everything live -> the ordinary fused path; output_dict and validation
+    k = ModelKernels()
+    ic = [t.clone().requires_grad_(True) for t in imgs]
+    tc = [t.clone().requires_grad_(True) for t in txts]
+    out = xt.ClipLoss(_kernels=k).forward_chunks(ic, tc, 11.0, output_dict=True)
+    assert set(out) == {"contrastive_loss"}
+    out["contrastive_loss"].backward()
+    assert len([c for c in k.calls if c[0] == "clip_bwd"]) == 1
+    with pytest.raises(ValueError):
+        xt.ClipLoss(_kernels=k).forward_chunks(ic, tc[:2], 11.0)
+
+
 def test_get_logits_slow_path_matches_reference_expression():
     I, T = torch.randn(6, 8), torch.randn(6, 8)
     li, lt = xt.ClipLoss().get_logits(I, T, torch.tensor(3.0))

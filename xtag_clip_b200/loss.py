@@ -350,6 +350,56 @@ class _FusedClipLoss(torch.autograd.Function):
         return d_img, d_txt, d_scale, None
 
 
+class _ChunkedClipLoss(torch.autograd.Function):
+    """Single-process loss over features given as CHUNKS of which only some carry gradient -- the gradient-accumulation
+    path of the reference (src/others/train_other.py:140-197): cached no-grad features of the other micro-batches are
+    concatenated with one live chunk and the loss is taken over the whole batch.  The forward is the full fused forward;
+    the backward forms gradients only for the live row / column blocks (two rectangular K2 calls per live chunk with
+    the saved full-batch log-sum-exps) instead of the full dI / dT the reference computes and then discards."""
+
+    @staticmethod
+    def forward(ctx, logit_scale, cfg, n, *chunks):
+        K = cfg.kernels
+        imgs, txts = chunks[:n], chunks[n:]
+        img_all = torch.cat([c.detach() for c in imgs], dim=0).contiguous()
+        txt_all = torch.cat([c.detach() for c in txts], dim=0).contiguous()
+        scale = _as_scale_tensor(logit_scale, img_all.device)
+        row_lse, col_lse, diag = K.clip_fwd(img_all, txt_all, scale, 0)
+        loss = K.clip_loss(row_lse, diag, col_lse, 0)
+        ctx.cfg, ctx.n = cfg, n
+        ctx.sizes = [int(c.shape[0]) for c in imgs]
+        ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
+        ctx.save_for_backward(img_all, txt_all, scale, row_lse, col_lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        img_all, txt_all, scale, row_lse, col_lse = ctx.saved_tensors
+        K, n = ctx.cfg.kernels, ctx.n
+        B = img_all.shape[0]
+        fdt = img_all.dtype
+        w_row, w_col, w_diag = 0.5 / B, 0.5 / B, 1.0 / B
+        need = ctx.needs_input_grad
+        grads = [None] * (3 + 2 * n)
+        if need[0] and ctx.scale_meta is not None:
+            # d(logit_scale) is a sum over the whole matrix: the dS producer alone, no gradient GEMM
+            _, _, ds = K.clip_bwd(img_all, txt_all, scale, 0, row_lse, col_lse, w_row, w_col, w_diag, g,
+                                  False, False, fdt)
+            shape, dtype = ctx.scale_meta
+            grads[0] = ds.to(dtype).reshape(shape)
+        lo = 0
+        for k, size in enumerate(ctx.sizes):
+            hi = lo + size
+            if need[3 + k]:           # image chunk k: rows [lo, hi) of S
+                grads[3 + k], _, _ = K.clip_bwd(img_all[lo:hi], txt_all, scale, lo, row_lse[lo:hi].contiguous(), col_lse,
+                                                w_row, w_col, w_diag, g, True, False, fdt)
+            if need[3 + n + k]:       # text chunk k: columns [lo, hi) of S = rows of S^T (row / column roles swap)
+                grads[3 + n + k], _, _ = K.clip_bwd(txt_all[lo:hi], img_all, scale, lo, col_lse[lo:hi].contiguous(),
+                                                    row_lse, w_col, w_row, w_diag, g, True, False, fdt)
+            lo = hi
+        return tuple(grads)
+
+
 # ------------------------------------------------------------------------------------------------
 # CUDA-graph replay of one loss step (launch-bound regimes: small batches, 8-GPU shards)
 # ------------------------------------------------------------------------------------------------
@@ -584,6 +634,26 @@ class ClipLoss(nn.Module):
             total_loss = self._forward_graphed(img, txt, logit_scale)
         else:
             total_loss = _FusedClipLoss.apply(img, txt, logit_scale, self._cfg())
+        return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+    def forward_chunks(self, image_chunks, text_chunks, logit_scale, output_dict=False):
+        """Gradient-accumulation form of `forward` (src/others/train_other.py:183-191 concatenates cached no-grad
+        features with one live chunk): `image_chunks` / `text_chunks` are equally long lists of [b_k, D] tensors whose
+        concatenation is the batch; chunks with `requires_grad=False` get no gradient work.  Equivalent to
+        `forward(torch.cat(image_chunks), torch.cat(text_chunks), logit_scale)`."""
+        if len(image_chunks) != len(text_chunks) or not image_chunks:
+            raise ValueError("image_chunks and text_chunks must be equally long, non-empty lists")
+        for a, c in zip(image_chunks, text_chunks):
+            if a.dim() != 2 or a.shape != c.shape or a.shape[1] != image_chunks[0].shape[1]:
+                raise ValueError("every image/text chunk pair must be [b_k, D] with one common D")
+        live = sum(int(t.requires_grad) for t in list(image_chunks) + list(text_chunks))
+        dts = {t.dtype for t in list(image_chunks) + list(text_chunks)}
+        if self.world_size > 1 or live == 2 * len(image_chunks) or len(dts) != 1 or not torch.is_grad_enabled():
+            # nothing to skip (or a sharded loss, whose gather needs whole tensors): the ordinary path
+            return self.forward(torch.cat(list(image_chunks), dim=0), torch.cat(list(text_chunks), dim=0), logit_scale,
+                                output_dict)
+        chunks = [c if c.dtype != torch.float16 else c.float() for c in list(image_chunks) + list(text_chunks)]
+        total_loss = _ChunkedClipLoss.apply(logit_scale, self._cfg(), len(image_chunks), *chunks)
         return {"contrastive_loss": total_loss} if output_dict else total_loss
 
     def _forward_graphed(self, img, txt, logit_scale):
