@@ -216,6 +216,12 @@ int xtag_asl_fwd(const void* x, int x_dtype, const float* y, int rows, int cols,
                  float gamma_neg, float gamma_pos, float clip, float eps,
                  float* loss_out, float* dx, int32_t* idx6, void* stream);
 
+/* Host-side views of the tcgen05 kernels' static tile schedule, for CPU tests (no device needed):
+ * tile -> (m tile, n tile, slab) exactly as the device code computes it, and the cluster size the launcher picks. */
+int xtag_debug_tile_coords(int M, int N, int slab, const int* order_host, int tile,
+                           int* m_blk, int* n_blk, int* slab_idx);
+int xtag_debug_pick_cluster(int M, int N, int tune);
+
 #ifdef __cplusplus
 }
 #endif

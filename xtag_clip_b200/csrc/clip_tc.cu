@@ -91,18 +91,18 @@ constexpr int kTunePrefetchMask = 0xff, kTuneStoreEvictFirst = 0x100, kTuneStrea
 // L2-resident while the groups stream past it even when the kernel also writes a large output (the dS producer writes
 // 2*BM*BN bytes per tile; without slabs every group pass re-fetched the whole B matrix from HBM and each k-block load
 // paid DRAM latency, which the 4-stage ring cannot hide: measured 77 % vs 95 % tensor-pipe activity).
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int slab, const int* slab_order, int& m_blk,
-                                            int& n_blk, int* slab_idx = nullptr) {
+__host__ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int slab, const int* slab_order,
+                                                     int& m_blk, int& n_blk, int* slab_idx = nullptr) {
   const int per_slab = num_m * slab;
   const int s = tile / per_slab;
   if (slab_idx) *slab_idx = s;
   const int n0 = (slab_order ? slab_order[s] : s) * slab;
-  const int ns = min(slab, num_n - n0);
+  const int ns = (slab < num_n - n0) ? slab : num_n - n0;
   const int r = tile - s * per_slab;
   const int per_group = kGroupM * ns;
   const int group = r / per_group;
   const int first_m = group * kGroupM;
-  const int gsize = min(num_m - first_m, kGroupM);
+  const int gsize = (num_m - first_m < kGroupM) ? num_m - first_m : kGroupM;
   const int in = r - group * per_group;
   m_blk = first_m + in % gsize;
   n_blk = n0 + in / gsize;
@@ -1046,3 +1046,21 @@ extern "C" int xtag_tc_gemm_nt(const void* A, const void* B, void* C, int c_dtyp
                                void* stream) {
   return xtag_tc_gemm(A, B, C, c_dtype, M, N, K, alpha, 0, 0, stream);
 }
+
+// Host-side view of the device tile schedule (tests/test_tile_schedule.py checks on the CPU that every tile is visited
+// exactly once, that the CTAs of a cluster share their n tile, and that a streamed forward walks the column blocks in
+// the requested order).  M, N in elements; slab in n tiles (0 = one slab); order = nullptr or a permutation of the
+// N / (slab * 256) column blocks.
+extern "C" int xtag_debug_tile_coords(int M, int N, int slab, const int* order, int tile, int* m_blk, int* n_blk,
+                                      int* slab_idx) {
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  if (M <= 0 || N <= 0 || tile < 0 || tile >= num_m * num_n || !m_blk || !n_blk) return XTAG_ERR_INVALID;
+  const int sl = (slab > 0 && slab < num_n) ? slab : num_n;
+  int s = 0;
+  tile_coords(tile, num_m, num_n, sl, order, *m_blk, *n_blk, &s);
+  if (slab_idx) *slab_idx = s;
+  return XTAG_OK;
+}
+
+// cluster size the launcher would pick for an [M, N] problem under tuning bits `tune`
+extern "C" int xtag_debug_pick_cluster(int M, int N, int tune) { return pick_cluster(M, N, tune); }
