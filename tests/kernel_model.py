@@ -80,6 +80,26 @@ class ModelKernels:
             col = st["col_out"]
         return row, col, st["diag"]
 
+    # K1 fused with the exchange: the contract is the plain forward over the whole gather buffer; the model checks
+    # the schedule arguments the host passes (own block first and not waited for, a permutation, one flag per block)
+    def supports_fwd_stream(self, A, blk_cols, nblk):
+        return self.fwd_blocks
+
+    def clip_fwd_stream(self, A, Bm_all, scale, label_offset, order, wait, blk_cols, ready_flags, epoch, col_out=None):
+        nblk = len(order)
+        assert sorted(order) == list(range(nblk)) and nblk * blk_cols == Bm_all.shape[0]
+        assert list(wait) == [False] + [True] * (nblk - 1), "only the rank's own block may be consumed without its flag"
+        assert label_offset == order[0] * blk_cols, "the first block visited must be the one holding the labels"
+        assert ready_flags.numel() == nblk and epoch.numel() == 1
+        self.calls.append(("clip_fwd_stream", tuple(A.shape), tuple(Bm_all.shape), int(label_offset), tuple(order)))
+        return self.clip_fwd(A, Bm_all, scale, label_offset, col_out=col_out)
+
+    def lse_combine_ptrs(self, ptrs, W, N):
+        return torch.logsumexp(torch.stack([_f64(p) for p in ptrs]), 0).float()
+
+    def sum_ptrs_bf16(self, ptrs, W, shape):
+        return sum(_f64(p) for p in ptrs).reshape(shape).to(torch.bfloat16)
+
     def lse_reduce_log2(self, parts):
         return (torch.logsumexp(_f64(parts) * math.log(2.0), 0)).float()
 
@@ -109,6 +129,9 @@ class ModelKernels:
         dS = g * (dS - w_diag * eye)
         dA = (s * dS @ B64).to(grad_dtype) if need_dA else None
         dB = (s * dS.T @ A64).to(grad_dtype) if need_dB else None
+        if dB is not None and dB_out is not None:
+            dB_out.copy_(dB)
+            dB = dB_out
         ds = torch.zeros((), dtype=torch.float32) if reuse_ds else (dS * raw).sum().float()
         if return_ws:
             return dA, dB, ds, "ws"

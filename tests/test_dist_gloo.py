@@ -167,3 +167,127 @@ def test_cliploss_world4_pipelined_groups_of_two():
         assert errs[2][3] == fwd_pipe          # the two reduction strategies launch the same forward blocks
     for p in procs:
         p.join(timeout=60)
+
+
+class FakeSymmExchange:
+    """Stand-in for xtag_clip_b200.symm.SymmExchange over gloo (TEST INFRASTRUCTURE): same methods and bookkeeping,
+    the peer-memory transfers replaced by collectives, so the host orchestration of the default multi-GPU path -- the
+    streamed forward and the symmetric reduce-scatter backward of xtag_clip_b200/loss.py -- runs in the CPU tests."""
+
+    def __init__(self, world, rank, b, D, dist):
+        self.W, self.r, self.b, self.D, self.B, self.dist = world, rank, b, D, world * b, dist
+        self.step = self.slot = 0
+        self.flags = torch.zeros(world, dtype=torch.int32)
+        self.epoch = torch.zeros(1, dtype=torch.int32)
+        self.col = torch.zeros(self.B, dtype=torch.float32)
+        self.dT = torch.zeros(self.B, D, dtype=torch.bfloat16)
+        self.log = []
+
+    def begin_step(self):
+        self.step += 1
+        self.slot = self.step & 1
+
+    def gather_streamed(self, x, out_all, pull_streams=1):
+        self.epoch.add_(1)
+        parts = [torch.empty_like(x) for _ in range(self.W)]
+        self.dist.all_gather(parts, x.contiguous())
+        for p in range(self.W):
+            out_all[p * self.b:(p + 1) * self.b].copy_(parts[p])
+        self.flags.fill_(int(self.epoch))
+        self.log.append("gather_streamed")
+        return [(self.r + j) % self.W for j in range(self.W)], [False] + [True] * (self.W - 1)
+
+    def end_gather(self, streamed=False):
+        self.log.append(("end_gather", streamed))
+
+    def col_buffer(self):
+        return self.col
+
+    def combine_cols(self, K):
+        parts = [torch.empty_like(self.col) for _ in range(self.W)]
+        self.dist.all_gather(parts, self.col)
+        return K.lse_combine_ptrs(parts, self.W, self.B)
+
+    def dT_buffer(self):
+        return self.dT
+
+    def reduce_scatter_begin(self):
+        self.log.append("reduce_scatter_begin")
+
+    def reduce_scatter_end(self, K):
+        parts = [torch.empty_like(self.dT) for _ in range(self.W)]
+        self.dist.all_gather(parts, self.dT)
+        lo, hi = self.r * self.b, (self.r + 1) * self.b
+        return K.sum_ptrs_bf16([p[lo:hi] for p in parts], self.W, (self.b, self.D))
+
+
+def _worker_symm(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import torch.distributed as dist
+    import oracle
+    import xtag_clip_b200 as xt
+    from xtag_clip_b200 import loss as xt_loss
+    from kernel_model import ModelKernels
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    try:
+        b, D, scale = 256, 16, 20.0                      # b is a multiple of 256: the streamed forward is eligible
+        gen = torch.Generator().manual_seed(5)
+        nrm = torch.nn.functional.normalize
+        I_all = nrm(torch.randn(world * b, D, generator=gen), dim=-1).bfloat16()
+        T_all = nrm(0.3 * I_all.float() + 0.7 * torch.randn(world * b, D, generator=gen), dim=-1).bfloat16()
+        Il = [I_all[r * b:(r + 1) * b].double() for r in range(world)]
+        Tl = [T_all[r * b:(r + 1) * b].double() for r in range(world)]
+        losses, dI, dT, ds = oracle.clip_loss_world(Il, Tl, scale, True, True)
+        fake = FakeSymmExchange(world, rank, b, D, dist)
+        xt_loss._Comm.symm_exchange = lambda self, x: fake if x.dtype == torch.bfloat16 else None
+        res = []
+        for streamed in (True, False):
+            k = ModelKernels()
+            I = I_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+            T = T_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+            s = torch.tensor(scale, requires_grad=True)
+            mod = xt.ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world, _kernels=k,
+                              stream_forward=streamed)
+            if not streamed:        # the per-block path pulls through gather_pipelined, which the fake does not model
+                xt_loss._Comm.symm_exchange = lambda self, x: None
+            loss = mod(I, T, s)
+            loss.backward()
+            res.append(dict(e_loss=rel_err(loss.item(), losses[rank].item()), e_di=rel_err(I.grad.float().numpy(), dI[rank].numpy()),
+                            e_dt=rel_err(T.grad.float().numpy(), dT[rank].numpy()), calls=list(k.calls), log=list(fake.log)))
+        q.put((rank, res, None))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,port", [(2, 29731), (4, 29732)])
+def test_streamed_forward_and_symmetric_backward_host_logic(world, port):
+    """The DEFAULT multi-GPU control flow (flag-gated streamed forward + symmetric-memory reduce-scatter backward) with
+    a gloo-backed stand-in for the peer-memory exchange: per-rank loss and gradients against the oracle's emulation of
+    the reference, the schedule handed to the kernel (ring order from the own block), and the backward's call pattern
+    (dS + dB GEMM into the exchange buffer, reduce-scatter started, dA GEMM reusing the staged dS, reduce finished)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_symm, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for _ in range(world):
+        rank, res, err = q.get(timeout=300)
+        assert err is None, err
+        st, blk = res
+        for r_ in (st, blk):
+            assert r_["e_loss"] < 1e-3 and r_["e_di"] < 2e-2 and r_["e_dt"] < 2e-2, (rank, r_["e_loss"], r_["e_di"], r_["e_dt"])
+        fwd = [c for c in st["calls"] if c[0] == "clip_fwd_stream"]
+        assert len(fwd) == 1 and fwd[0][1] == (256, 16) and fwd[0][2] == (world * 256, 16) and fwd[0][3] == rank * 256
+        assert fwd[0][4] == tuple((rank + j) % world for j in range(world))
+        bwd = [c for c in st["calls"] if c[0] == "clip_bwd"]
+        assert len(bwd) == 2 and all(c[1] == (256, 16) and c[2] == (world * 256, 16) and c[3] == rank * 256 for c in bwd)
+        assert st["log"] == ["gather_streamed", ("end_gather", True), "reduce_scatter_begin"]
+    for p in procs:
+        p.join(timeout=60)
