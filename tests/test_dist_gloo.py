@@ -197,6 +197,19 @@ class FakeSymmExchange:
         self.log.append("gather_streamed")
         return [(self.r + j) % self.W for j in range(self.W)], [False] + [True] * (self.W - 1)
 
+    def gather_pushed(self, x):
+        self.epoch.add_(1)
+        parts = [torch.empty_like(x) for _ in range(self.W)]
+        self.dist.all_gather(parts, x.contiguous())
+        gbuf = torch.cat(parts, dim=0)
+        self.flags.fill_(int(self.epoch))
+        self._pushed = True
+        self.log.append("gather_pushed")
+        return gbuf, [(self.r - j) % self.W for j in range(self.W)], [False] + [True] * (self.W - 1), self.flags
+
+    def push_step_done(self):
+        self.log.append("push_step_done")
+
     def end_gather(self, streamed=False):
         self.log.append(("end_gather", streamed))
 
@@ -245,15 +258,18 @@ def _worker_symm(rank, world, port, q):
         fake = FakeSymmExchange(world, rank, b, D, dist)
         xt_loss._Comm.symm_exchange = lambda self, x: fake if x.dtype == torch.bfloat16 else None
         res = []
-        for streamed in (True, False):
+        for streamed in (True, False, "push"):
             k = ModelKernels()
             I = I_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
             T = T_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
             s = torch.tensor(scale, requires_grad=True)
             mod = xt.ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world, _kernels=k,
-                              stream_forward=streamed)
+                              stream_forward=bool(streamed), exchange="push" if streamed == "push" else "pull")
             if not streamed:        # the per-block path pulls through gather_pipelined, which the fake does not model
                 xt_loss._Comm.symm_exchange = lambda self, x: None
+            else:
+                fake.log.clear()
+                xt_loss._Comm.symm_exchange = lambda self, x: fake if x.dtype == torch.bfloat16 else None
             loss = mod(I, T, s)
             loss.backward()
             res.append(dict(e_loss=rel_err(loss.item(), losses[rank].item()), e_di=rel_err(I.grad.float().numpy(), dI[rank].numpy()),
@@ -280,8 +296,8 @@ def test_streamed_forward_and_symmetric_backward_host_logic(world, port):
     for _ in range(world):
         rank, res, err = q.get(timeout=300)
         assert err is None, err
-        st, blk = res
-        for r_ in (st, blk):
+        st, blk, push = res
+        for r_ in (st, blk, push):
             assert r_["e_loss"] < 1e-3 and r_["e_di"] < 2e-2 and r_["e_dt"] < 2e-2, (rank, r_["e_loss"], r_["e_di"], r_["e_dt"])
         fwd = [c for c in st["calls"] if c[0] == "clip_fwd_stream"]
         assert len(fwd) == 1 and fwd[0][1] == (256, 16) and fwd[0][2] == (world * 256, 16) and fwd[0][3] == rank * 256
@@ -289,5 +305,9 @@ def test_streamed_forward_and_symmetric_backward_host_logic(world, port):
         bwd = [c for c in st["calls"] if c[0] == "clip_bwd"]
         assert len(bwd) == 2 and all(c[1] == (256, 16) and c[2] == (world * 256, 16) and c[3] == rank * 256 for c in bwd)
         assert st["log"] == ["gather_streamed", ("end_gather", True), "reduce_scatter_begin"]
+        # push exchange (experimental): blocks arrive r-1, r-2, ...; the backward ends with the slot-release barrier
+        fwd = [c for c in push["calls"] if c[0] == "clip_fwd_stream"]
+        assert len(fwd) == 1 and fwd[0][4] == tuple((rank - j) % world for j in range(world))
+        assert push["log"] == ["gather_pushed", ("end_gather", True), "reduce_scatter_begin", "push_step_done"]
     for p in procs:
         p.join(timeout=60)
