@@ -181,6 +181,7 @@ class FakeSymmExchange:
         self.epoch = torch.zeros(1, dtype=torch.int32)
         self.col = torch.zeros(self.B, dtype=torch.float32)
         self.dT = torch.zeros(self.B, D, dtype=torch.bfloat16)
+        self._pushed = False
         self.log = []
 
     def begin_step(self):

@@ -27,6 +27,7 @@ for GradScaler-scaled losses).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -318,7 +319,7 @@ class _FusedClipLoss(torch.autograd.Function):
                     d_img = d_img.to(fdt)
                 if need_t:
                     d_txt = cfg.comm.reduce_scatter_sum(d_txt_all).to(fdt)
-            if ctx.symm is not None and getattr(ctx.symm[0], "_pushed", False):
+            if ctx.symm is not None and ctx.symm[0]._pushed:
                 ctx.symm[0].push_step_done()
         elif cfg.local_loss:
             ds = torch.zeros((), dtype=torch.float32, device=img.device)
@@ -561,8 +562,7 @@ class ClipLoss(nn.Module):
         self._stream_fwd = stream_forward
         self._pull_streams = pull_streams
         # "pull" (validated) or "push" (experimental: no start-of-step barrier); default from XTAG_EXCHANGE
-        import os as _os
-        self._exchange = exchange or _os.environ.get("XTAG_EXCHANGE", "pull")
+        self._exchange = exchange or os.environ.get("XTAG_EXCHANGE", "pull")
         if self._exchange not in ("pull", "push"):
             raise ValueError(f"exchange must be 'pull' or 'push', got {self._exchange!r}")
         self._cuda_graph = cuda_graph

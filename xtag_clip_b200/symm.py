@@ -72,6 +72,9 @@ class SymmExchange:
         # step's epoch value (a device counter, so a captured step replays with fresh values)
         self.flags = torch.zeros(world, dtype=torch.int32, device=device)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self._streamed_two = False        # the last streamed gather forked the second copy stream
+        self._pushed = False              # the push exchange is in use (its backward ends with a slot-release barrier)
+        self.gbuf = None                  # push exchange: peer-writable gather buffers, allocated on first use
 
     # ---- schedule ---------------------------------------------------------------------------------------------
     def _blocks(self) -> List[Tuple[int, int, List[int]]]:
@@ -156,7 +159,7 @@ class SymmExchange:
     def _push_buffers(self):
         """Peer-writable gather buffers [2][B, D] and per-slot ready flags [2][W] (lazily: only the push exchange
         needs them)."""
-        if getattr(self, "gbuf", None) is None:
+        if self.gbuf is None:
             import torch.distributed._symmetric_memory as symm_mem
             grp = self._grp
             dev = self.feat.device
@@ -205,7 +208,7 @@ class SymmExchange:
     def end_gather(self, streamed: bool = False):
         """the pull streams must be drained before the next barrier on s1 (orders the next overwrite of a slot).
         The streamed gather never forks s2 (waiting on it would pull an un-captured stream into a graph capture)."""
-        if not streamed or getattr(self, "_streamed_two", False):
+        if not streamed or self._streamed_two:
             self.s1.wait_stream(self.s2)
         torch.cuda.current_stream().wait_stream(self.s1)
 
