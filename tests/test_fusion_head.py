@@ -1,7 +1,7 @@
 """TQN fusion head + DQNCOSLoss: the oracle restatement and the drop-in's host logic
 against fixtures the REFERENCE produced (tests/golden/fusion.npz, oracle/make_golden.py:golden_fusion).  On CPU the
 kernels are the contract model (tests/kernel_model.py); the GPU variants at the bottom run the real K4 / LSE kernels and
-are gated behind XTAG_EXPERIMENTAL=1 until they have been validated on a B200."""
+run on every GPU test pass (validated on a B200 in round 2)."""
 import os
 import sys
 
@@ -139,13 +139,8 @@ def test_from_reference_live():
     assert rel_err(head(mem, qf), ref(mem, qf)) < 1e-9
 
 
-# ------------------------------------------------------------------------------------------------ GPU (gated)
-gpu_experimental = pytest.mark.skipif(os.environ.get("XTAG_EXPERIMENTAL") != "1",
-                                      reason="fusion head on the GPU: not yet validated on a B200 (set XTAG_EXPERIMENTAL=1)")
-
-
+# ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@gpu_experimental
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
 def test_fusion_head_gpu(G, dtype, tol):
     pre, seed, d, layers = _case(G, 2)                                      # d_model 512: head dim 128 (tensor-core K4)
@@ -161,7 +156,6 @@ def test_fusion_head_gpu(G, dtype, tol):
 
 
 @pytest.mark.gpu
-@gpu_experimental
 def test_dqn_cos_loss_gpu(G):
     for n in range(3):
         x = torch.from_numpy(G[f"ce{n}_x"]).float().cuda().requires_grad_(True)

@@ -249,8 +249,6 @@ def test_config1_heads_on_reference_encoder_outputs(golden_dir):
     assert rel_err(l2, ref[0]) < 1e-3 and rel_err(I2.grad, ref[1]) < 2e-2 and rel_err(T2.grad, ref[2]) < 2e-2
 
 
-@pytest.mark.skipif(os.environ.get("XTAG_EXPERIMENTAL") != "1",
-                    reason="forward_chunks on the GPU: not yet validated on a B200 (set XTAG_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
 def test_forward_chunks_gradient_accumulation_gpu(dtype, tol):
     """train_other.py:140-197 on the real kernels: cached no-grad chunks + one live chunk against the oracle."""

@@ -15,7 +15,7 @@ with `--use-fusion`.  HOST COMPOSITION over kerne
     closed form (softmax_row + softmax_col - 2 I) / (2B).
 
 Status: host logic and parity are covered on CPU against fixtures the reference produced (tests/golden/fusion.npz);
-the GPU tests of this module are gated (XTAG_EXPERIMENTAL=1) until they have run on a B200.
+the GPU tests of this module (tests/test_fusion_head.py, `-m gpu`) pass on a B200.
 """
 from __future__ import annotations
 
