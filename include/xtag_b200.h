@@ -66,9 +66,18 @@ uint64_t    xtag_launch_count(void);
  *   bits 12, 13  DIAGNOSTICS, wrong results: skip the dS staging + store / skip only the dS TMA store
  *   bits 14, 15  thread-block clusters of 2 / 4 CTAs along M, the shared B tile TMA-multicast to the cluster
  *   bits [16,24) n-slab width (in 256-column tiles) of the tile schedule (0 = one slab)
+ *   bit 24       do NOT use the CTA-pair kernels (tcgen05.mma.cta_group::2, 256 x 256 tiles per pair of SMs, 6-stage
+ *                operand ring); default: pair kernels whenever the problem has more than 128 rows
+ *   bits 25, 26  L2 evict_last on the B / A operand tile loads
  * Initial value: environment variable XTAG_TC_TUNE (0x800 if unset).  set returns the previous value. */
 int         xtag_set_tune(int bits);
 int         xtag_get_tune(void);
+/* Budget of the bounded device-side waits (mbarrier phases; the ready flags of xtag_clip_fwd_stream, where a rank
+ * legitimately waits for slow peers).  A wait that exceeds it prints a diagnostic and traps, which fails the launch
+ * instead of hanging the GPU.  Default 1 800 000 ms (longer than the 10 min default of the NCCL process group the
+ * exchange replaces); initial value from XTAG_SPIN_TIMEOUT_MS.  Applies to launches made after the call; do not call
+ * it inside a stream capture. */
+int         xtag_set_spin_timeout_ms(long long ms);
 int         xtag_prof_enable(int on);
 int         xtag_prof_read(int* tags_host, float* ms_host, double* flops_host, int cap);
 

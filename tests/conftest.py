@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# bounded device-side waits (csrc/tc_ptx.cuh): a protocol bug must fail a test within seconds, not after the 30 min
+# production budget
+os.environ.setdefault("XTAG_SPIN_TIMEOUT_MS", "20000")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")

@@ -23,6 +23,7 @@ SIGNATURES = {
     "xtag_launch_count": (c_uint64, []),
     "xtag_set_tune": (c_int, [c_int]),
     "xtag_get_tune": (c_int, []),
+    "xtag_set_spin_timeout_ms": (c_int, [ctypes.c_longlong]),
     "xtag_prof_enable": (c_int, [c_int]),
     "xtag_prof_read": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "xtag_l2norm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),

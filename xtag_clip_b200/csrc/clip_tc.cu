@@ -30,18 +30,27 @@ namespace xtag {
 using namespace ptx;
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kStages = 4;
 constexpr int kABytes = BM * BK * 2;          // 16 KB
-constexpr int kBBytes = BN * BK * 2;          // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + 32 * kEpiWarps;   // 384
 constexpr int kTmemCols = 512;
 constexpr int kGroupM = 16;
 constexpr int kEpiScratchFloats = 2 /*acc*/ * 2 /*half*/ * 4 /*quadrant*/ * 128;   // 8 KB
 constexpr int kOutStageBytes = kEpiWarps * 2048;   // per epilogue warp: one 32-row x 64-byte tile for the dS TMA store
-constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 256 /*barriers*/ + kEpiScratchFloats * 4 +
-                           kOutStageBytes;
+// Shared-memory geometry per CTA.  CG = 1: one CTA per 128 x 256 tile (tcgen05.mma.cta_group::1).  CG = 2: a CTA PAIR
+// (two SMs of one TPC) per 256 x 256 tile (tcgen05.mma.cta_group::2, M = 256): every CTA stages its own 128 rows of A
+// and only ITS HALF of the B tile, so a k-block costs 32 KB instead of 48 KB of shared memory (6 ring stages instead of
+// 4: 50 % more look-ahead against L2 / DRAM latency) and each SM reads a third less operand data per MMA.
+template <int CG>
+struct Geo {
+  static constexpr int kBRows = BN / CG;
+  static constexpr int kBBytes = kBRows * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (CG == 2) ? 6 : 4;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 256 /*barriers*/ +
+                                    kEpiScratchFloats * 4 + kOutStageBytes;
+};
+constexpr int kMaxStages = 6;
 
 enum { EPI_LSE = 0, EPI_DS = 1, EPI_STORE = 2 };
 
@@ -82,7 +91,10 @@ constexpr int kTunePrefetchMask = 0xff, kTuneStoreEvictFirst = 0x100, kTuneStrea
               kTuneCluster2 = 0x4000,       // clusters of 2 CTAs along M with TMA multicast of the shared B tile
               kTuneCluster4 = 0x8000,       // clusters of 4
               kTuneDbgNoDsStore = 0x1000,   // diagnostics only (wrong results): dS tile neither staged nor stored
-              kTuneDbgNoDsTma = 0x2000;     // diagnostics only (wrong results): dS tile staged in smem, TMA store skipped
+              kTuneDbgNoDsTma = 0x2000,     // diagnostics only (wrong results): dS tile staged in smem, TMA store skipped
+              kTuneNoPair = 0x1000000,      // do NOT use the CTA-pair (cta_group::2) kernels
+              kTuneBEvictLast = 0x2000000,  // B operand tiles: L2 evict_last
+              kTuneAEvictLast = 0x4000000;  // A operand tiles: L2 evict_last
 
 // Static tile schedule.  Tiles are ordered  n-slab  >  group of kGroupM m tiles  >  n tile inside the slab  >  m tile
 // inside the group, so that at any time the CTAs work on a [kGroupM m tiles] x [~#SM / kGroupM n tiles] patch (operand
@@ -92,17 +104,18 @@ constexpr int kTunePrefetchMask = 0xff, kTuneStoreEvictFirst = 0x100, kTuneStrea
 // 2*BM*BN bytes per tile; without slabs every group pass re-fetched the whole B matrix from HBM and each k-block load
 // paid DRAM latency, which the 4-stage ring cannot hide: measured 77 % vs 95 % tensor-pipe activity).
 __host__ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int slab, const int* slab_order,
-                                                     int& m_blk, int& n_blk, int* slab_idx = nullptr) {
+                                                     int& m_blk, int& n_blk, int* slab_idx = nullptr,
+                                                     int group_m = kGroupM) {
   const int per_slab = num_m * slab;
   const int s = tile / per_slab;
   if (slab_idx) *slab_idx = s;
   const int n0 = (slab_order ? slab_order[s] : s) * slab;
   const int ns = (slab < num_n - n0) ? slab : num_n - n0;
   const int r = tile - s * per_slab;
-  const int per_group = kGroupM * ns;
+  const int per_group = group_m * ns;
   const int group = r / per_group;
-  const int first_m = group * kGroupM;
-  const int gsize = (num_m - first_m < kGroupM) ? num_m - first_m : kGroupM;
+  const int first_m = group * group_m;
+  const int gsize = (num_m - first_m < group_m) ? num_m - first_m : group_m;
   const int in = r - group * per_group;
   m_blk = first_m + in % gsize;
   n_blk = n0 + in / gsize;
@@ -162,7 +175,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 //             serve the column sums after one multiply and a 31-shuffle transpose-reduce.
 //   Exact unless an element lies more than 2^-kRange below W (it would flush to zero while possibly dominating
 //   its own column): such chunks -- a 32x32 block spanning > 83 nats -- take the exact two-exp path.
-template <bool FULL>
+// "accumulator drained": in CTA-pair mode both CTAs' epilogue warps report to the LEADER's barrier (its MMA thread
+// writes both halves of the next accumulator)
+template <int CG>
+__device__ __forceinline__ void arrive_tempty(uint32_t tempty) {
+  if constexpr (CG == 2) mbar_arrive_cluster(tempty, 0);
+  else                   mbar_arrive(tempty);
+}
+
+template <bool FULL, int CG>
 __device__ __forceinline__ void lse_tile(const EpiParams& ep, uint32_t taddr, float* scratch, int gi, int n_base,
                                          int m_blk, int n_blk, int h, int q, int lane, int M, int N,
                                          uint32_t tempty, int bar_id) {
@@ -262,7 +283,7 @@ __device__ __forceinline__ void lse_tile(const EpiParams& ep, uint32_t taddr, fl
   // TMEM reads of this warp are complete: release the accumulator before the cross-warp combine
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(tempty);
+  if (lane == 0) arrive_tempty<CG>(tempty);
   named_bar_sync(bar_id, 128);
   {
     const int c = q * 32 + lane;
@@ -410,7 +431,10 @@ __device__ __forceinline__ void store_tile(const EpiParams& ep, uint32_t taddr, 
 // shared memory of all CL CTAs.  Per CTA the TMA unit then moves BM + BN/CL rows per k-block instead of BM + BN and
 // the L2 -> SM operand traffic drops by the same factor (measured: the TMA/L2 request rate, not the tensor pipe, is
 // what the 128x256 tiles saturate first; an added L2 prefetch stream slows the kernels by 1.4x).
-template <int EPI, bool A_MN, bool B_MN, int CL>
+// CG = 2: CTA-pair kernel (see Geo): cluster = the pair, rank 0 = leader.  Both CTAs run a TMA producer (own A rows, own
+// half of B, bytes credited to the leader's "full" barrier) and the epilogue of their 128 accumulator rows; only the
+// leader's MMA thread issues tcgen05.mma.cta_group::2 and its commits are multicast onto both CTAs' barriers.
+template <int EPI, bool A_MN, bool B_MN, int CL, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, int M, int N, int K, const __grid_constant__ EpiParams ep) {
@@ -422,6 +446,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* stage_base = smem;
   // layout: [operand ring | dS store staging (both 1024-byte aligned: swizzle patterns use absolute address bits)
   //          | mbarriers + TMEM pointer (256 B) | epilogue scratch]
+  static_assert(CG == 1 || CL == 1, "the CTA pair is the cluster: no additional multicast clusters");
+  using G = Geo<CG>;
+  constexpr int kStages = G::kStages, kStageBytes = G::kStageBytes;
+  constexpr bool kClustered = (CL > 1) || (CG == 2);
   uint8_t* out_stage = smem + kStages * kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kOutStageBytes);
   uint64_t* full_bar = bars;                      // [kStages]
@@ -433,9 +461,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  // scheduled tiles: BM*CG rows x BN columns (a CTA pair works on two vertically adjacent 128-row blocks)
+  const int num_m = (M + BM * CG - 1) / (BM * CG), num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = (K + BK - 1) / BK;
+  constexpr int kGroup = kGroupM / CG;            // same operand footprint per wave in both modes
+  const int tile_first = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int slab_req = (ep.tune >> 16) & 0xff;                    // n tiles per slab of the tile schedule (0: one slab)
   const bool streamed = (EPI == EPI_LSE) && ep.blk_tiles > 0;
   const int slab = streamed ? ep.blk_tiles : ((slab_req > 0 && slab_req < num_n) ? slab_req : num_n);
@@ -448,50 +480,72 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(smem_u32(&full_bar[i]), 1);
-      mbar_init(smem_u32(&empty_bar[i]), CL);      // a slot is rewritten by every CTA of the cluster (B multicast)
+      // multicast clusters: a slot is rewritten by every CTA of the cluster (B multicast), each of which commits;
+      // CTA pair: one multicast commit of the leader arrives once on each CTA's barrier
+      mbar_init(smem_u32(&empty_bar[i]), CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tfull_bar[i]), 1);
-      mbar_init(smem_u32(&tempty_bar[i]), kEpiWarps);
+      mbar_init(smem_u32(&tempty_bar[i]), kEpiWarps * CG);   // pair: both CTAs' epilogue warps report to the leader
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(smem_u32(tmem_ptr), kTmemCols);
-    tmem_relinquish();
+    tmem_alloc<CG>(smem_u32(tmem_ptr), kTmemCols);
+    tmem_relinquish<CG>();
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CL > 1) cluster_sync();            // peers' barriers are initialised before any multicast can arrive
+  if constexpr (kClustered) cluster_sync();        // peers' barriers are initialised before any multicast can arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  [[maybe_unused]] const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0u;
-  [[maybe_unused]] constexpr uint16_t kClMask = (uint16_t)((1u << CL) - 1u);
+  [[maybe_unused]] const uint32_t cta_rank = kClustered ? cluster_ctarank() : 0u;
+  [[maybe_unused]] constexpr uint16_t kClMask = (uint16_t)((1u << (CL * CG)) - 1u);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const int pf_dist = ep.tune & kTunePrefetchMask;
+      const int pf_dist = (CG == 1) ? (ep.tune & kTunePrefetchMask) : 0;
       // bit 9: the A operand of the plain GEMMs is the staged dS, read exactly once: mark it evict_first so that the
       // stream does not push the re-used B operand (the feature matrix) out of L2
-      const uint64_t a_policy = (EPI == EPI_STORE && (ep.tune & kTuneStreamAEvictFirst)) ? l2_policy_evict_first() : 0;
-      // box (64 inner elements x rows) origin of operand X for block index blk and k-block kb
+      const uint64_t a_policy = (EPI == EPI_STORE && (ep.tune & kTuneStreamAEvictFirst)) ? l2_policy_evict_first()
+                                : (ep.tune & kTuneAEvictLast)                            ? l2_policy_evict_last()
+                                                                                         : 0;
+      const uint64_t b_policy = (ep.tune & kTuneBEvictLast) ? l2_policy_evict_last() : 0;
+      // one 64-element-wide box of operand X into this CTA's shared memory; pair mode credits the leader's barrier
+      auto load_box = [&](uint32_t dst, const CUtensorMap* tm, uint32_t fb, int c0, int c1, uint64_t policy) {
+        if constexpr (CG == 2) {
+          if (policy) tma_load_2d_pair_hint(dst, tm, fb, c0, c1, policy);
+          else        tma_load_2d_pair(dst, tm, fb, c0, c1);
+        } else {
+          if (policy) tma_load_2d_hint(dst, tm, fb, c0, c1, policy);
+          else        tma_load_2d(dst, tm, fb, c0, c1);
+        }
+      };
+      // m_blk: this CTA's own 128-row block
       auto load_a = [&](uint32_t sa, uint32_t fb, int m_blk, int kb) {
         if constexpr (A_MN) {
 #pragma unroll
-          for (int u = 0; u < BM / 64; ++u) {
-            if (a_policy) tma_load_2d_hint(sa + u * (BK * 128), &tmA, fb, m_blk * BM + u * 64, kb * BK, a_policy);
-            else          tma_load_2d(sa + u * (BK * 128), &tmA, fb, m_blk * BM + u * 64, kb * BK);
-          }
+          for (int u = 0; u < BM / 64; ++u) load_box(sa + u * (BK * 128), &tmA, fb, m_blk * BM + u * 64, kb * BK, a_policy);
         } else {
-          if (a_policy) tma_load_2d_hint(sa, &tmA, fb, kb * BK, m_blk * BM, a_policy);
-          else          tma_load_2d(sa, &tmA, fb, kb * BK, m_blk * BM);
+          load_box(sa, &tmA, fb, kb * BK, m_blk * BM, a_policy);
         }
       };
       auto load_b = [&](uint32_t sb, uint32_t fb, int n_blk, int kb) {
-        if constexpr (CL > 1) {
+        if constexpr (CG == 2) {
+          // this CTA's half of the B tile (N rows [rank*128, rank*128 + 128) of the 256), stored at the start of its
+          // own B slot: the pair MMA reads the two halves from the two CTAs
+          if constexpr (B_MN) {
+            constexpr int per = BN / 64 / 2;
+#pragma unroll
+            for (int uu = 0; uu < per; ++uu)
+              load_box(sb + uu * (BK * 128), &tmB, fb, n_blk * BN + ((int)cta_rank * per + uu) * 64, kb * BK, b_policy);
+          } else {
+            load_box(sb, &tmB, fb, kb * BK, n_blk * BN + (int)cta_rank * (BN / 2), b_policy);
+          }
+        } else if constexpr (CL > 1) {
           // this CTA's 1/CL slice of the shared B tile, multicast to the whole cluster
           if constexpr (B_MN) {
             constexpr int per = BN / 64 / CL;
@@ -506,9 +560,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else if constexpr (B_MN) {
 #pragma unroll
-          for (int u = 0; u < BN / 64; ++u) tma_load_2d(sb + u * (BK * 128), &tmB, fb, n_blk * BN + u * 64, kb * BK);
+          for (int u = 0; u < BN / 64; ++u) load_box(sb + u * (BK * 128), &tmB, fb, n_blk * BN + u * 64, kb * BK, b_policy);
         } else {
-          tma_load_2d(sb, &tmB, fb, kb * BK, n_blk * BN);
+          load_box(sb, &tmB, fb, kb * BK, n_blk * BN, b_policy);
         }
       };
       auto prefetch = [&](int m_blk, int n_blk, int kb) {
@@ -527,9 +581,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
       int slab_seen = -1;
       const int epoch = (streamed && ep.ready_flags) ? ep.epoch_p[0] : 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         int m_blk, n_blk, s_idx;
-        tile_coords(tile, num_m, num_n, slab, slab_order, m_blk, n_blk, &s_idx);
+        tile_coords(tile, num_m, num_n, slab, slab_order, m_blk, n_blk, &s_idx, kGroup);
+        if constexpr (CG == 2) m_blk = m_blk * 2 + (int)cta_rank;
         if (streamed && s_idx != slab_seen) {
           // first tile of this CTA in a new column block: its rows of the gather buffer must have landed (the copy
           // engine writes the flag right behind the block); order the TMA (async proxy) reads after the acquire
@@ -540,7 +595,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           slab_seen = s_idx;
         }
         int m_nxt = -1, n_nxt = -1;
-        if (pf_dist && tile + (int)gridDim.x < num_tiles) tile_coords(tile + gridDim.x, num_m, num_n, slab, slab_order, m_nxt, n_nxt);
+        if (pf_dist && tile + tile_step < num_tiles)
+          tile_coords(tile + tile_step, num_m, num_n, slab, slab_order, m_nxt, n_nxt, nullptr, kGroup);
         for (int kb = 0; kb < num_k; ++kb) {
           if (pf_dist == 0xff) {
             // de-duplicated next-tile prefetch: the CTAs of a wave share operand tiles (16 CTAs per B tile, ~9 per A
@@ -574,7 +630,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_arrive_expect_tx(fb, kStageBytes);
+          // pair mode: the leader expects both CTAs' bytes on its barrier (the peer's boxes may complete first: the
+          // transaction count is signed within a phase)
+          if (CG == 1 || cta_rank == 0) mbar_arrive_expect_tx(fb, kStageBytes * CG);
           const uint32_t sa = smem_u32(stage_base + stage * kStageBytes);
           load_a(sa, fb, m_blk, kb);
           load_b(sa + kABytes, fb, n_blk, kb);
@@ -582,10 +640,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && (CG == 1 || cta_rank == 0)) {
     // ===================================== MMA issuer =======================================
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = make_idesc_bf16_f32(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // K-major : rows of 64 K-elements (128 B), 8-row swizzle atoms 1024 B apart (SBO); LBO unused
       // MN-major: 64 MN-elements per 128 B row, one row per K index; 8 K-rows = one 1024 B atom (SBO),
       //           the next 64 MN-elements live in the next TMA box, BK*128 B further (LBO)
@@ -601,7 +659,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -612,14 +670,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t da = make_smem_desc(sa, a_hi);
           const uint64_t db = make_smem_desc(sa + kABytes, b_hi);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(d_tmem, da + (uint64_t)k * a_step, db + (uint64_t)k * b_step, idesc, (uint32_t)((kb | k) != 0));
+          for (int k = 0; k < BK / 16; ++k) {
+            if constexpr (CG == 2)
+              umma_bf16_pair(d_tmem, da + (uint64_t)k * a_step, db + (uint64_t)k * b_step, idesc, (uint32_t)((kb | k) != 0));
+            else
+              umma_bf16(d_tmem, da + (uint64_t)k * a_step, db + (uint64_t)k * b_step, idesc, (uint32_t)((kb | k) != 0));
+          }
           // frees the smem slot when the MMAs retire -- in every CTA of the cluster, whose producers all write it
-          if constexpr (CL > 1) umma_commit_mc(smem_u32(&empty_bar[stage]), kClMask);
-          else                  umma_commit(smem_u32(&empty_bar[stage]));
+          if constexpr (CG == 2)     umma_commit_pair(smem_u32(&empty_bar[stage]), kClMask);
+          else if constexpr (CL > 1) umma_commit_mc(smem_u32(&empty_bar[stage]), kClMask);
+          else                       umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&tfull_bar[acc]));           // accumulator ready for the epilogue
+        // accumulator ready for the epilogue (pair: of both CTAs, each waits on its own barrier)
+        if constexpr (CG == 2) umma_commit_pair(smem_u32(&tfull_bar[acc]), kClMask);
+        else                   umma_commit(smem_u32(&tfull_bar[acc]));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -634,9 +699,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t acc_phase = 0;
     float dscale_acc = 0.f;
     [[maybe_unused]] const uint64_t store_policy = (ep.tune & kTuneStoreEvictFirst) ? l2_policy_evict_first() : 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
       int m_blk, n_blk;
-      tile_coords(tile, num_m, num_n, slab, slab_order, m_blk, n_blk);
+      tile_coords(tile, num_m, num_n, slab, slab_order, m_blk, n_blk, nullptr, kGroup);
+      if constexpr (CG == 2) m_blk = m_blk * 2 + (int)cta_rank;
       const int gi = m_blk * BM + q * 32 + lane;          // this thread's row
       const int n_base = n_blk * BN + h * 128;            // first column of this warp's half
       // interior tiles (no ragged edge in this warp's 32 x 128 block) take the branch-free code
@@ -646,11 +712,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tfull = smem_u32(&tfull_bar[acc]);
       const uint32_t tempty = smem_u32(&tempty_bar[acc]);
 
-      if constexpr (EPI == EPI_LSE) {
+      if (CG == 2 && m_blk * BM >= M) {
+        // odd number of 128-row blocks: the pair's second CTA holds no rows of the last tile row.  It still takes part
+        // in the accumulator hand-shake (the leader's MMA wrote zeros into its tensor memory).
         mbar_wait(tfull, acc_phase);
         tc_fence_after();
-        if (interior) lse_tile<true>(ep, taddr, scratch, gi, n_base, m_blk, n_blk, h, q, lane, M, N, tempty, bar_id);
-        else          lse_tile<false>(ep, taddr, scratch, gi, n_base, m_blk, n_blk, h, q, lane, M, N, tempty, bar_id);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_tempty<CG>(tempty);
+      } else if constexpr (EPI == EPI_LSE) {
+        mbar_wait(tfull, acc_phase);
+        tc_fence_after();
+        if (interior) lse_tile<true, CG>(ep, taddr, scratch, gi, n_base, m_blk, n_blk, h, q, lane, M, N, tempty, bar_id);
+        else          lse_tile<false, CG>(ep, taddr, scratch, gi, n_base, m_blk, n_blk, h, q, lane, M, N, tempty, bar_id);
       } else if constexpr (EPI == EPI_DS) {
         // stage the per-column terms of this half in smem before touching TMEM:
         //   [0,128)   two-exp path: exponent offsets, w_col * 2^(v - cl2) = 2^(v - (cl2 - log2 w_col));
@@ -715,14 +789,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty);
+        if (lane == 0) arrive_tempty<CG>(tempty);
       } else {
         mbar_wait(tfull, acc_phase);
         tc_fence_after();
         store_tile(ep, taddr, gi, n_base, M, N);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty);
+        if (lane == 0) arrive_tempty<CG>(tempty);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -736,10 +810,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (CL > 1) cluster_sync();            // no CTA exits while a peer may still multicast into it
+  if constexpr (kClustered) cluster_sync();        // no CTA exits while a peer may still multicast into it / read its smem
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc<CG>(tmem_base, kTmemCols);
   }
 }
 
@@ -793,9 +867,22 @@ static int make_store_tmap_bf16(CUtensorMap* tm, void* base, int rows, int cols,
   return XTAG_OK;
 }
 
-template <int EPI, bool A_MN, bool B_MN, int CL>
+// per-device "already done" flags of one kernel instantiation (one process may drive several GPUs)
+struct PerDevice {
+  int v[64] = {};
+  int& here() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return v[dev & 63];
+  }
+};
+
+template <int EPI, bool A_MN, bool B_MN, int CL, int CG>
 static int launch_tc_cl(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiParams& ep,
                         cudaStream_t st, int grid, int* grid_used) {
+  constexpr int kSmemBytes = Geo<CG>::kSmemBytes;
+  constexpr int kCluster = CL * CG;
+  XTAG_CUDA(sync_spin_timeout());
   CUtensorMap tmA, tmB, tmC;
   memset(&tmC, 0, sizeof(tmC));
   if (EPI == EPI_DS) {
@@ -805,13 +892,13 @@ static int launch_tc_cl(const void* A, long lda, const void* B, long ldb, int M,
   int rc = A_MN ? make_tmap_bf16(&tmA, A, K, M, lda, BK) : make_tmap_bf16(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
   // K-major B: each CTA of a cluster fetches BN / CL rows of the shared tile
-  rc = B_MN ? make_tmap_bf16(&tmB, B, K, N, ldb, BK) : make_tmap_bf16(&tmB, B, N, K, ldb, BN / CL);
+  rc = B_MN ? make_tmap_bf16(&tmB, B, K, N, ldb, BK) : make_tmap_bf16(&tmB, B, N, K, ldb, BN / kCluster);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XTAG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, A_MN, B_MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  static PerDevice attr_set;
+  if (!attr_set.here()) {
+    XTAG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<EPI, A_MN, B_MN, CL, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kSmemBytes));
-    attr_set = true;
+    attr_set.here() = 1;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);
@@ -820,29 +907,29 @@ static int launch_tc_cl(const void* A, long lda, const void* B, long ldb, int M,
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.x = kCluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
-  if (CL > 1) {
+  cfg.numAttrs = kCluster > 1 ? 1 : 0;
+  if (kCluster > 1) {
     // a persistent kernel needs every cluster co-resident: GPCs with a number of free SMs that is not a multiple of
-    // CL leave SMs unused, so the grid is sized by what the device can actually hold
-    static int max_clusters = 0;
-    if (max_clusters == 0) {
+    // the cluster size leave SMs unused, so the grid is sized by what the device can actually hold
+    static PerDevice max_clusters;
+    if (max_clusters.here() == 0) {
       int n = 0;
-      XTAG_CUDA(cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<EPI, A_MN, B_MN, CL>, &cfg));
-      XTAG_REQUIRE(n > 0, XTAG_ERR_CUDA, "no cluster of %d CTAs with %d bytes of shared memory fits on this device", CL,
-                   kSmemBytes);
-      max_clusters = n;
+      XTAG_CUDA(cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<EPI, A_MN, B_MN, CL, CG>, &cfg));
+      XTAG_REQUIRE(n > 0, XTAG_ERR_CUDA, "no cluster of %d CTAs with %d bytes of shared memory fits on this device",
+                   kCluster, kSmemBytes);
+      max_clusters.here() = n;
     }
-    if (grid > max_clusters * CL) grid = max_clusters * CL;
+    if (grid > max_clusters.here() * kCluster) grid = max_clusters.here() * kCluster;
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
   }
   if (grid_used) *grid_used = grid;
   {
     ProfScope prof(EPI, 2.0 * (double)M * (double)N * (double)K, st);
-    XTAG_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, A_MN, B_MN, CL>, tmA, tmB, tmC, M, N, K, ep));
+    XTAG_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<EPI, A_MN, B_MN, CL, CG>, tmA, tmB, tmC, M, N, K, ep));
   }
   XTAG_CHECK_LAUNCH();
   return XTAG_OK;
@@ -858,19 +945,29 @@ static int pick_cluster(int M, int N, int tune) {
   return cl;
 }
 
+// CTA-pair kernels whenever the problem has at least two 128-row blocks (tune bit 24 turns them off)
+static bool pick_pair(int M, int tune) { return !(tune & kTuneNoPair) && M > BM; }
+
 template <int EPI, bool A_MN, bool B_MN>
 static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiParams& ep_in,
                      cudaStream_t st, int* grid_used = nullptr) {
   EpiParams ep = ep_in;
   ep.tune = tc_tune();
-  const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int num_n = (N + BN - 1) / BN;
+  if (pick_pair(M, ep.tune)) {
+    const int num_pairs = ((M + 2 * BM - 1) / (2 * BM)) * num_n;
+    int grid = num_sms() & ~1;
+    if (grid > 2 * num_pairs) grid = 2 * num_pairs;
+    return launch_tc_cl<EPI, A_MN, B_MN, 1, 2>(A, lda, B, ldb, M, N, K, ep, st, grid, grid_used);
+  }
+  const int num_tiles = ((M + BM - 1) / BM) * num_n;
   const int cl = pick_cluster(M, N, ep.tune);
   int grid = num_sms();
   if (grid > num_tiles) grid = num_tiles;
   grid -= grid % cl;
-  if (cl == 4) return launch_tc_cl<EPI, A_MN, B_MN, 4>(A, lda, B, ldb, M, N, K, ep, st, grid, grid_used);
-  if (cl == 2) return launch_tc_cl<EPI, A_MN, B_MN, 2>(A, lda, B, ldb, M, N, K, ep, st, grid, grid_used);
-  return launch_tc_cl<EPI, A_MN, B_MN, 1>(A, lda, B, ldb, M, N, K, ep, st, grid, grid_used);
+  if (cl == 4) return launch_tc_cl<EPI, A_MN, B_MN, 4, 1>(A, lda, B, ldb, M, N, K, ep, st, grid, grid_used);
+  if (cl == 2) return launch_tc_cl<EPI, A_MN, B_MN, 2, 1>(A, lda, B, ldb, M, N, K, ep, st, grid, grid_used);
+  return launch_tc_cl<EPI, A_MN, B_MN, 1, 1>(A, lda, B, ldb, M, N, K, ep, st, grid, grid_used);
 }
 
 int launch_lse_reduce(const float* parts, int P, int n, float in_mul, float out_mul, float* out, cudaStream_t st);

@@ -21,16 +21,15 @@ void set_error(const char* fmt, ...) {
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      return 148;
+  static std::atomic<int> cached[64];   // per device (zero-initialised)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int n = cached[dev & 63].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cached[dev & 63].store(n, std::memory_order_relaxed);
   }
-  return cached;
+  return n;
 }
 
 // runtime tuning bits of the tcgen05 kernels (see EpiParams::tune in clip_tc.cu); initialised once from the
@@ -41,11 +40,26 @@ int tc_tune() {
   int t = g_tune.load(std::memory_order_relaxed);
   if (t < 0) {
     const char* e = getenv("XTAG_TC_TUNE");
-    t = e ? (int)strtol(e, nullptr, 0) & 0xffffff : kDefaultTune;
+    t = e ? (int)strtol(e, nullptr, 0) & 0x7fffffff : kDefaultTune;
     g_tune.store(t, std::memory_order_relaxed);
   }
   return t;
 }
+
+// spin budget of the bounded device-side waits (tc_ptx.cuh); generation 0 = the environment / default value
+static std::atomic<long long> g_spin_ms{-1};
+static std::atomic<int> g_spin_gen{0};
+unsigned long long spin_timeout_ns() {
+  long long ms = g_spin_ms.load(std::memory_order_relaxed);
+  if (ms < 0) {
+    const char* e = getenv("XTAG_SPIN_TIMEOUT_MS");
+    ms = e ? strtoll(e, nullptr, 0) : 1800LL * 1000LL;
+    if (ms <= 0) ms = 1800LL * 1000LL;
+    g_spin_ms.store(ms, std::memory_order_relaxed);
+  }
+  return (unsigned long long)ms * 1000000ull;
+}
+int spin_timeout_gen() { return g_spin_gen.load(std::memory_order_relaxed); }
 
 struct ProfRec {
   int tag;
@@ -107,11 +121,18 @@ int xtag_prof_read(int* tags, float* ms, double* work, int cap) {
 
 int xtag_set_tune(int bits) {
   const int old = xtag::tc_tune();
-  xtag::g_tune.store(bits & 0xffffff, std::memory_order_relaxed);
+  xtag::g_tune.store(bits & 0x7fffffff, std::memory_order_relaxed);
   return old;
 }
 
 int xtag_get_tune(void) { return xtag::tc_tune(); }
+
+int xtag_set_spin_timeout_ms(long long ms) {
+  XTAG_REQUIRE(ms > 0, XTAG_ERR_INVALID, "xtag_set_spin_timeout_ms: the budget must be positive (got %lld)", ms);
+  xtag::g_spin_ms.store(ms, std::memory_order_relaxed);
+  xtag::g_spin_gen.fetch_add(1, std::memory_order_relaxed);
+  return XTAG_OK;
+}
 
 int xtag_version(void) { return XTAG_ABI_VERSION; }
 

@@ -45,12 +45,53 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (visible as a launch failure) instead of hanging the GPU box.
+// Spin budget of the bounded waits below, in nanoseconds of %globaltimer.  A wait that exceeds it is a protocol bug
+// (mbarriers) or a peer that never delivered its block (ready flags): the kernel then reports and traps, which surfaces
+// as a launch failure on the host instead of a hung GPU.  Inside a streamed forward a rank legitimately waits for slow
+// peers (data-loader stalls, rank-0-only evaluation or checkpointing), so the default budget is 30 min -- longer than
+// the 10 min default timeout of the NCCL process group the exchange replaces; xtag_set_spin_timeout_ms() /
+// XTAG_SPIN_TIMEOUT_MS shorten it for tests.  One copy per translation unit and device; `apply_spin_timeout` (called by
+// xtag_set_spin_timeout_ms and once before a translation unit's first launch) writes it.
+static __device__ unsigned long long g_spin_timeout_ns = 1800ull * 1000ull * 1000ull * 1000ull;
+
+}  // namespace ptx
+unsigned long long spin_timeout_ns();   // core.cu: current budget (xtag_set_spin_timeout_ms / XTAG_SPIN_TIMEOUT_MS)
+int spin_timeout_gen();                 // bumped by every change
+namespace ptx {
+// Brings this translation unit's device copy up to date on the current device.  A synchronous symbol copy: it only
+// happens when the budget changed since the last launch from this unit (never inside a stream capture unless the
+// caller changes the budget there).
+static inline cudaError_t sync_spin_timeout() {
+  static int applied[64];
+  static bool init = false;
+  if (!init) {
+    for (int i = 0; i < 64; ++i) applied[i] = -1;
+    init = true;
+  }
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const int gen = spin_timeout_gen();
+  if (applied[dev & 63] == gen) return cudaSuccess;
+  const unsigned long long ns = spin_timeout_ns();
+  e = cudaMemcpyToSymbol(g_spin_timeout_ns, &ns, sizeof(ns));
+  if (e == cudaSuccess) applied[dev & 63] = gen;
+  return e;
+}
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Bounded wait on an mbarrier phase.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_ns();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 60000000000LL) {   // ~30 s at 2 GHz (a streamed forward legitimately waits for slow peers)
+    if ((++spins & 0x3ff) == 0 && global_ns() - t0 > g_spin_timeout_ns) {
       printf("xtag: mbarrier timeout block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
@@ -58,17 +99,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // Spin until the 32-bit word at `p` equals `want` (written by a copy engine or a peer GPU after the data it guards).
-// Bounded (~30 s) like the mbarrier waits.
 __device__ __forceinline__ void wait_flag_eq(const int* p, int want) {
   int v;
   asm volatile("ld.acquire.sys.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   if (v == want) return;
-  const long long t0 = clock64();
+  const unsigned long long t0 = global_ns();
   while (true) {
     __nanosleep(200);
     asm volatile("ld.acquire.sys.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     if (v == want) return;
-    if (clock64() - t0 > 60000000000LL) {
+    if (global_ns() - t0 > g_spin_timeout_ns) {
       printf("xtag: ready-flag timeout block %d flag %p = %d, expected %d\n", blockIdx.x, p, v, want);
       __trap();
     }
@@ -105,6 +145,32 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst_smem, const CUtensor
       "[%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
       : "memory");
+}
+// CTA-pair (cta_group::2) loads: the box lands in THIS CTA's shared memory, the transaction bytes are credited to the
+// mbarrier at the same offset in the pair's LEADER (even) CTA, whose MMA thread consumes both halves.  Shared-window
+// addresses of a clustered launch carry the CTA's rank-in-pair in bit 24; clearing it names the leader's copy.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0,
+                                                      int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+// arrive on the mbarrier at shared-memory offset `bar` of cluster CTA `cta` (may be this CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 remote;\n\t"
+      "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n\t}\n"
+      ::"r"(bar), "r"(cta) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -150,14 +216,24 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05 -----------------------------------------------------------------------------------------
+// CG = 1: one CTA owns its tensor memory.  CG = 2: a CTA pair (two SMs of one TPC) allocates the same columns in both
+// SMs; the same warp index of BOTH CTAs executes alloc / relinquish / dealloc.
+template <int CG = 1>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  if constexpr (CG == 2)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
 }
+template <int CG = 1>
 __device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (CG == 2) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  else                   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
+template <int CG = 1>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else                   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -174,6 +250,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 // all previously issued tcgen05.mma of this thread arrive on `bar` when complete
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// CTA-pair MMA (M = 256): issued by one thread of the LEADER CTA only.  Each CTA supplies its own 128 rows of A and its
+// half of the N rows of B from the same shared-memory offsets; the accumulator rows 0-127 land in the leader's tensor
+// memory, rows 128-255 in the peer's, at the same columns.
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued CTA-pair MMAs arrive on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
 // same, arriving on the mbarrier at this shared-memory offset in every CTA of `cta_mask`

@@ -310,6 +310,7 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
   const int nw = (Lq + 15) / 16;
   const size_t q_bytes = ((size_t)NCH * 16 * nw * 128 + 1023) & ~(size_t)1023;
   const size_t smem = 1024 + q_bytes + 2 * (2 * NCH * XA_KT * 128) + 64;
+  XTAG_CUDA(sync_spin_timeout());
   XTAG_CUDA(cudaFuncSetAttribute(xattn_fwd_mma_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   xattn_fwd_mma_kernel<NCH><<<b * heads, 32 * nw, smem, st>>>(tq, tk, tv, (__nv_bfloat16*)o, lse, Lq, Lk, heads, sl2, p,
                                                               seed, offset);
@@ -996,6 +997,7 @@ static int launch_bwd_fused(const void* q, const void* k, const void* v, const v
   const size_t q_pad = ((size_t)NCH * 16 * NW * 128 + 1023) & ~(size_t)1023;
   const size_t smem = 1024 + 2 * q_pad + 2 * (2 * NCH * XA_KT * 128) + NCH * XA_KT * 128 + 2 * (16 * NW * 64) + 64 +
                       16 * NW * 4;
+  XTAG_CUDA(sync_spin_timeout());
   XTAG_CUDA(cudaFuncSetAttribute(xattn_bwd_fused_kernel<NCH, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   xattn_bwd_fused_kernel<NCH, NW><<<b * heads, 32 * NW, smem, st>>>(
       tq, tk, tv, tdo, tdk, tdv, (const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, lse, (__nv_bfloat16*)dq, Lq, Lk,
@@ -1035,6 +1037,7 @@ static int launch_bwd(const void* q, const void* k, const void* v, const void* o
   {
     const size_t q_pad = ((size_t)NCH * 16 * nw * 128 + 1023) & ~(size_t)1023;
     const size_t smem = 1024 + 2 * q_pad + 2 * (2 * NCH * XA_KT * 128) + 64 + 16 * nw * 4;
+    XTAG_CUDA(sync_spin_timeout());
     XTAG_CUDA(cudaFuncSetAttribute(xattn_bwd_dq_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     xattn_bwd_dq_kernel<NCH><<<b * heads, 32 * nw, smem, st>>>(tq, tk, tv, tdo, (const __nv_bfloat16*)o,
                                                                (const __nv_bfloat16*)d_o, lse, (__nv_bfloat16*)dq, delta,
