@@ -69,7 +69,7 @@ uint64_t    xtag_launch_count(void);
  *   bit 24       do NOT use the CTA-pair kernels (tcgen05.mma.cta_group::2, 256 x 256 tiles per pair of SMs, 6-stage
  *                operand ring); default: pair kernels whenever the problem has more than 128 rows
  *   bits 25, 26  L2 evict_last on the B / A operand tile loads
- * Initial value: environment variable XTAG_TC_TUNE (0x800 if unset).  set returns the previous value. */
+ * Initial value: environment variable XTAG_TC_TUNE (0x200800 if unset).  set returns the previous value. */
 int         xtag_set_tune(int bits);
 int         xtag_get_tune(void);
 /* Budget of the bounded device-side waits (mbarrier phases; the ready flags of xtag_clip_fwd_stream, where a rank

@@ -181,12 +181,16 @@ def test_clip_wide_dynamic_range(MK):
         assert rel_err(dA, dAm) < 2e-2 and rel_err(dB, dBm) < 2e-2
 
 
-@pytest.mark.parametrize("tune", [0x000, 0x400, 0x008, 0x004, 0x300, 0x30c])
+# bit 24 (0x1000000) selects the single-CTA kernels; clear = CTA-pair kernels (cta_group::2), the default
+@pytest.mark.parametrize("tune", [0x000, 0x1000000, 0x400, 0x1000400, 0x1000008, 0x1000004, 0x300, 0x100030c,
+                                  0x6200900, 0x20000, 0x1020000])
 @pytest.mark.parametrize("M,N,D,off,scale", [(130, 300, 72, 100, 14.285714), (512, 1024, 512, 256, 100.0),
-                                             (1024, 1024, 1024, 0, 30.0)])
+                                             (1024, 1024, 1024, 0, 30.0), (330, 1320, 136, 64, 14.285714)])
 def test_tc_tune_bits_parity(MK, tune, M, N, D, off, scale):
-    """Every runtime tuning bit of the tcgen05 kernels (xtag_set_tune: L2 prefetch distance, L2 cache hints, the
-    one-exp / two-exp dS epilogue) is a pure performance knob: forward and backward stay within the bf16 bars."""
+    """Every runtime tuning bit of the tcgen05 kernels (xtag_set_tune: CTA-pair vs single-CTA kernels, L2 prefetch
+    distance, L2 cache hints, n-slab schedule, the one-exp / two-exp dS epilogue) is a pure performance knob: forward and
+    backward stay within the bf16 bars.  M = 330 has an odd number of 128-row blocks: the pair's second CTA idles on
+    the last tile row."""
     from xtag_clip_b200.kernels import CudaKernels
     K = CudaKernels(impl=2)
     old = K.lib.xtag_set_tune(tune)
@@ -274,11 +278,14 @@ def test_clip_fwd_blocks_deferred_reductions(K, MK, M, D, blocks, own):
     assert rel_err(row, r1) < 1e-6 and rel_err(col, c1) < 1e-6 and torch.equal(diag, d1)
 
 
-@pytest.mark.parametrize("tune", [0x4000, 0x8000])
-@pytest.mark.parametrize("M,N,Kd", [(256, 512, 128), (512, 768, 4096), (4096, 1024, 4096), (1024, 1000, 1000), (384, 256, 64)])
+@pytest.mark.parametrize("tune", [0x1004000, 0x1008000, 0x0, 0x1000000])
+@pytest.mark.parametrize("M,N,Kd", [(256, 512, 128), (512, 768, 4096), (4096, 1024, 4096), (1024, 1000, 1000), (384, 256, 64),
+                                    (640, 264, 200)])
 def test_tc_gemm_cluster_multicast(K, tune, M, N, Kd):
-    """Thread-block clusters along M with the shared B tile TMA-multicast (tune bits 14 / 15), all three operand
-    layouts; shapes whose m-tile count is not a multiple of the cluster size fall back to smaller clusters."""
+    """Thread-block clusters along M with the shared B tile TMA-multicast (tune bits 14 / 15 on the single-CTA kernels),
+    the CTA-pair kernels (tune 0) and the plain single-CTA kernels, all three operand layouts; shapes whose m-tile count
+    is not a multiple of the cluster size fall back to smaller clusters; 384 / 640 rows = an odd number of 128-row
+    blocks for the pair kernels."""
     old = K.lib.xtag_set_tune(tune)
     try:
         g = torch.Generator().manual_seed(M + N + Kd)

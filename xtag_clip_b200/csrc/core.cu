@@ -35,7 +35,10 @@ int num_sms() {
 // runtime tuning bits of the tcgen05 kernels (see EpiParams::tune in clip_tc.cu); initialised once from the
 // environment variable XTAG_TC_TUNE, overridable with xtag_set_tune()
 static std::atomic<int> g_tune{-1};
-static constexpr int kDefaultTune = 0x800;   // single-pass K4 backward (validated on B200: 1.4-2x faster than the two-kernel path)
+// defaults: bit 11 = single-pass K4 backward (1.4-2x faster than the two-kernel path); n-slab of 32 tiles (8192 columns
+// = 16 MB of the B operand stay L2-resident while the m groups stream past: -1.8 % step time in the sustained power
+// state, profiles/r2_sustained_ab.json); CTA-pair kernels on (bit 24 clear)
+static constexpr int kDefaultTune = 0x200800;
 int tc_tune() {
   int t = g_tune.load(std::memory_order_relaxed);
   if (t < 0) {

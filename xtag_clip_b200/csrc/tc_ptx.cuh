@@ -164,12 +164,14 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst_smem, const C
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
-// arrive on the mbarrier at shared-memory offset `bar` of cluster CTA `cta` (may be this CTA)
+// arrive on the mbarrier at shared-memory offset `bar` of cluster CTA `cta` (may be this CTA).  Default semantics
+// (.release.cta): an explicit .release.cluster compiles to MEMBAR.ALL.CTA + ERRBAR, measured as 9 % of the dS kernel's
+// issue slots; the tensor-memory reads this arrive publishes are ordered by tcgen05.wait::ld + fence::before_thread_sync
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 remote;\n\t"
       "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n\t}\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t}\n"
       ::"r"(bar), "r"(cta) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
