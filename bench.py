@@ -212,7 +212,8 @@ def run_ours(args):
     log_scale = torch.tensor(2.659260036932778, device=dev, requires_grad=True)     # ln(1/0.07)
     # cuda_graph=True: the public option that replays a captured step (the 8-GPU shard is launch-bound otherwise)
     loss_mod = xt.ClipLoss(local_loss=world > 1, gather_with_grad=world > 1, cache_labels=True, rank=rank,
-                           world_size=world, cuda_graph=not args.no_graph, pull_streams=args.pull_streams)
+                           world_size=world, cuda_graph=not args.no_graph, pull_streams=args.pull_streams,
+                           exchange=args.exchange)
     loss_eager = xt.ClipLoss(local_loss=world > 1, gather_with_grad=world > 1, cache_labels=True, rank=rank,
                              world_size=world)
 
@@ -409,8 +410,10 @@ def main():
     ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
-    ap.add_argument("--pull-streams", type=int, default=1,
-                    help="copy streams of the streamed feature gather (2 = experimental, see symm.gather_streamed)")
+    ap.add_argument("--pull-streams", type=int, default=2,
+                    help="copy streams of the streamed feature exchange (see symm.gather_streamed / gather_pushed)")
+    ap.add_argument("--exchange", default=None, choices=["pull", "push"],
+                    help="feature exchange of the sharded forward (default: the library default / XTAG_EXCHANGE)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

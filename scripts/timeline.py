@@ -25,7 +25,8 @@ def main():
     I = I.to(dev).requires_grad_(True); T = T.to(dev).requires_grad_(True)
     ls = torch.tensor(2.659, device=dev, requires_grad=True)
     mod = xt.ClipLoss(local_loss=world > 1, gather_with_grad=world > 1, cache_labels=True, rank=rank, world_size=world,
-                      cuda_graph=bool(int(os.environ.get("XGRAPH", "0"))))
+                      cuda_graph=bool(int(os.environ.get("XGRAPH", "0"))), exchange=os.environ.get("XEXCH") or None,
+                      pull_streams=int(os.environ.get("XPS", "2")))
 
     def step():
         I.grad = T.grad = ls.grad = None

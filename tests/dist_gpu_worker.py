@@ -83,6 +83,75 @@ def main():
         for name, a, bb in zip(("loss", "dI", "dT", "ds"), res[0], res[1]):
             if rel(a, bb) > 1e-5:
                 failures.append(f"cuda_graph it={it} rank={rank}: {name} differs from eager by {rel(a, bb):.2e}")
+    # The SHIPPED shard shapes (BASELINE config 5: b = 4096, D = 1024; config 4: global 8192, D = 768), performance
+    # mode, both exchanges, eager and CUDA-graph replay, against the already validated single-GPU ClipLoss on the
+    # concatenated batch: mean of the rank losses == global loss, rank feature gradients == W x the global gradient's
+    # slice, sum of the rank d(logit_scale) == W x the global one ("Gradient scaling").
+    small = os.environ.get("XTAG_DIST_SMALL") == "1"
+    shapes = [("C5", 4096, 1024), ("C4", 8192 // world, 768)]
+    if small:
+        shapes = [("C5/4", 1024, 1024), ("C4/4", 2048 // world, 768)]
+    for name, b, D in shapes:
+        B = b * world
+        g = torch.Generator().manual_seed(31 + D)
+        I_all = torch.nn.functional.normalize(torch.randn(B, D, generator=g), dim=-1)
+        T_all = torch.nn.functional.normalize(0.5 * I_all + 0.5 * torch.randn(B, D, generator=g), dim=-1).bfloat16()
+        I_all = I_all.bfloat16()
+        Ig = I_all.to(dev).requires_grad_(True)
+        Tg = T_all.to(dev).requires_grad_(True)
+        sg = torch.tensor(14.285714, device=dev, requires_grad=True)
+        lg = xt.ClipLoss()(Ig, Tg, sg)
+        lg.backward()
+        lo, hi = rank * b, (rank + 1) * b
+        for exch in ("pull", "push"):
+            for cg in (False, True):
+                mod = xt.ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world, exchange=exch,
+                                  cuda_graph=cg)
+                for it in range(3 if cg else 2):        # replays after the capture; slot parity of the eager path
+                    I = I_all[lo:hi].to(dev).requires_grad_(True)
+                    T = T_all[lo:hi].to(dev).requires_grad_(True)
+                    s = torch.tensor(14.285714, device=dev, requires_grad=True)
+                    loss = mod(I, T, s)
+                    loss.backward()
+                    tag = f"{name} b={b} D={D} W={world} {exch} graph={cg} it={it} rank={rank}"
+                    lm = loss.detach().clone()
+                    dist.all_reduce(lm)
+                    lm /= world
+                    e = (rel(lm, lg), rel(I.grad, world * Ig.grad[lo:hi]), rel(T.grad, world * Tg.grad[lo:hi]))
+                    if e[0] > 1e-3 or e[1] > 2e-2 or e[2] > 2e-2:
+                        failures.append(f"{tag}: mean loss {e[0]:.2e} dI {e[1]:.2e} dT {e[2]:.2e}")
+                    tot = s.grad.detach().clone()
+                    dist.all_reduce(tot)
+                    ref_tot = world * float(sg.grad)
+                    if abs(tot.item() - ref_tot) > 2e-2 * abs(ref_tot) + 5e-5:
+                        failures.append(f"{tag}: dscale sum {tot.item():.6e} vs {ref_tot:.6e}")
+                path = mod.last_path
+                if path["exchange"] != f"symmetric-memory {exch}" or path["cuda_graph"] != cg:
+                    failures.append(f"{tag}: fell back to {path}")
+        del Ig, Tg, lg
+        torch.cuda.empty_cache()
+    # rank skew: the flag-gated K1 of the push exchange waits inside the kernel for a late peer (here 1.5 s; the spin
+    # budget of the tests is 20 s) and still produces the right loss
+    b, D = 512, 256
+    g = torch.Generator().manual_seed(5)
+    I_all = torch.nn.functional.normalize(torch.randn(b * world, D, generator=g), dim=-1).bfloat16()
+    T_all = torch.nn.functional.normalize(0.3 * I_all.float() + 0.7 * torch.randn(b * world, D, generator=g), dim=-1).bfloat16()
+    mod = xt.ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world, exchange="push")
+    vals = []
+    for it in range(3):
+        if it == 1 and rank == world - 1:
+            torch.cuda.synchronize()
+            import time
+            time.sleep(1.5)
+        I = I_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+        T = T_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+        loss = mod(I, T, torch.tensor(14.285714, device=dev))
+        loss.backward()
+        vals.append((loss.detach().clone(), I.grad.clone()))
+    torch.cuda.synchronize()
+    for it in (1, 2):
+        if rel(vals[it][0], vals[0][0]) > 1e-6 or rel(vals[it][1], vals[0][1]) > 1e-6:
+            failures.append(f"skewed push step {it} rank={rank}: differs from the unskewed step")
     n_fail = torch.tensor([len(failures)], device=dev)
     dist.all_reduce(n_fail)
     for f in failures:

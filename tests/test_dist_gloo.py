@@ -182,6 +182,7 @@ class FakeSymmExchange:
         self.col = torch.zeros(self.B, dtype=torch.float32)
         self.dT = torch.zeros(self.B, D, dtype=torch.bfloat16)
         self._pushed = False
+        self.bwd_pending = False
         self.log = []
 
     def begin_step(self):
@@ -198,7 +199,7 @@ class FakeSymmExchange:
         self.log.append("gather_streamed")
         return [(self.r + j) % self.W for j in range(self.W)], [False] + [True] * (self.W - 1)
 
-    def gather_pushed(self, x):
+    def gather_pushed(self, x, streams=2):
         self.epoch.add_(1)
         parts = [torch.empty_like(x) for _ in range(self.W)]
         self.dist.all_gather(parts, x.contiguous())
@@ -209,6 +210,7 @@ class FakeSymmExchange:
         return gbuf, [(self.r - j) % self.W for j in range(self.W)], [False] + [True] * (self.W - 1), self.flags
 
     def push_step_done(self):
+        self.bwd_pending = False
         self.log.append("push_step_done")
 
     def end_gather(self, streamed=False):
@@ -275,6 +277,24 @@ def _worker_symm(rank, world, port, q):
             loss.backward()
             res.append(dict(e_loss=rel_err(loss.item(), losses[rank].item()), e_di=rel_err(I.grad.float().numpy(), dI[rank].numpy()),
                             e_dt=rel_err(T.grad.float().numpy(), dT[rank].numpy()), calls=list(k.calls), log=list(fake.log)))
+        # push-exchange guard: the gather buffer of a pushed forward is peer-writable and saved for its backward, so a
+        # forward issued while that backward is outstanding, and a no_grad forward, must take the pull exchange
+        fake.log.clear()
+        fake.bwd_pending = False
+        xt_loss._Comm.symm_exchange = lambda self, x: fake if x.dtype == torch.bfloat16 else None
+        mod = xt.ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world, _kernels=ModelKernels(),
+                          exchange="push")
+        I = I_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+        T = T_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+        s = torch.tensor(scale, requires_grad=True)
+        l1 = mod(I, T, s)
+        l2 = mod(I, T, s)
+        with torch.no_grad():
+            mod(I, T, s)
+        l1.backward()
+        l3 = mod(I, T, s)
+        res.append(dict(log=list(fake.log), same=float((l1 - l2).abs() + (l1 - l3).abs()),
+                        e_di=rel_err(I.grad.float().numpy(), dI[rank].numpy())))
         q.put((rank, res, None))
     except Exception:  # pragma: no cover
         import traceback
@@ -297,7 +317,11 @@ def test_streamed_forward_and_symmetric_backward_host_logic(world, port):
     for _ in range(world):
         rank, res, err = q.get(timeout=300)
         assert err is None, err
-        st, blk, push = res
+        st, blk, push, guard = res
+        names = [x if isinstance(x, str) else x[0] for x in guard["log"]]
+        assert [n for n in names if n.startswith("gather")] == ["gather_pushed", "gather_streamed", "gather_streamed",
+                                                                "gather_pushed"], names
+        assert names.count("push_step_done") == 1 and guard["same"] < 1e-6 and guard["e_di"] < 2e-2
         for r_ in (st, blk, push):
             assert r_["e_loss"] < 1e-3 and r_["e_di"] < 2e-2 and r_["e_dt"] < 2e-2, (rank, r_["e_loss"], r_["e_di"], r_["e_dt"])
         fwd = [c for c in st["calls"] if c[0] == "clip_fwd_stream"]

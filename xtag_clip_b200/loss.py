@@ -164,6 +164,7 @@ class _Cfg:
     stream_fwd: bool = True
     pull_streams: int = 1
     exchange: str = "pull"
+    will_backward: bool = True       # a backward of this forward is expected (grad mode on, some input requires grad)
 
 
 def _as_scale_tensor(logit_scale, device) -> torch.Tensor:
@@ -196,8 +197,15 @@ class _FusedClipLoss(torch.autograd.Function):
                 # K1 fused with the exchange: ONE persistent launch consumes the gather buffer block by block, gated by
                 # the ready flags the copy stream writes behind each block
                 sx.begin_step()
-                if cfg.exchange == "push":
-                    txt_all, order, wait, flags = sx.gather_pushed(txt)
+                # push exchange: the gather buffer is peer-writable and saved for the backward, which releases it with
+                # a barrier.  A forward without a backward to come (no_grad / evaluation), or one issued while another
+                # forward's backward is still outstanding, therefore takes the pull exchange (private gather buffer);
+                # every rank sees the same call sequence and so takes the same branch.
+                pushed = cfg.exchange == "push" and cfg.will_backward and not sx.bwd_pending
+                if pushed:
+                    txt_all, order, wait, flags = sx.gather_pushed(txt, max(cfg.pull_streams, 1))
+                    sx.bwd_pending = True
+                    ctx.pushed = sx
                 else:
                     order, wait = sx.gather_streamed(txt, txt_all, cfg.pull_streams)
                     flags = sx.flags
@@ -262,6 +270,8 @@ class _FusedClipLoss(torch.autograd.Function):
         loss = K.clip_loss(row_lse, diag, col_lse, off)
         if not hasattr(ctx, "symm"):
             ctx.symm = None
+        if not hasattr(ctx, "pushed"):
+            ctx.pushed = None
         ctx.cfg, ctx.off, ctx.b = cfg, off, b
         ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
         ctx.save_for_backward(img, txt, scale, row_lse, col_lse, img_all, txt_all)
@@ -319,8 +329,8 @@ class _FusedClipLoss(torch.autograd.Function):
                     d_img = d_img.to(fdt)
                 if need_t:
                     d_txt = cfg.comm.reduce_scatter_sum(d_txt_all).to(fdt)
-            if ctx.symm is not None and ctx.symm[0]._pushed:
-                ctx.symm[0].push_step_done()
+            if ctx.pushed is not None:
+                ctx.pushed.push_step_done()     # releases the peer-writable gather buffer of this step
         elif cfg.local_loss:
             ds = torch.zeros((), dtype=torch.float32, device=img.device)
             if need_i or need_s:
@@ -449,20 +459,33 @@ class _GraphedStep:
             with torch.cuda.graph(self.bwd, pool=self.pool):
                 self.s_grads = torch.autograd.grad(self.s_loss, self.inputs, self.s_g)
             self.n_bwd = _lib.launch_count() - n0
+        self.pending = False            # a replayed forward whose backward has not run yet
+
+    def input_slots(self):
+        """The static input tensors of the captured step.  A producer that writes its features straight into them
+        (e.g. `l2_normalize(x, out=slot)`) and passes them to the loss skips the per-step input copies."""
+        return self.s_img.detach(), self.s_txt.detach()
 
     def run_forward(self, img, txt, logit_scale):
-        self.s_img.detach().copy_(img)
-        self.s_txt.detach().copy_(txt)
+        # the saved activations of a captured step live in ONE set of static buffers: a second forward before the
+        # first one's backward would silently overwrite them (the caller checks `pending` and runs eagerly instead)
+        assert not self.pending
+        if img.data_ptr() != self.s_img.data_ptr():
+            self.s_img.detach().copy_(img)
+        if txt.data_ptr() != self.s_txt.data_ptr():
+            self.s_txt.detach().copy_(txt)
         if self.scale_is_tensor:
             self.s_scale.detach().copy_(logit_scale.detach())
         self.fwd.replay()
         self._lib.note_replayed(self.n_fwd)
+        self.pending = self.bwd is not None
         return self.s_loss.detach().clone()
 
     def run_backward(self, g):
         self.s_g.copy_(g)
         self.bwd.replay()
         self._lib.note_replayed(self.n_bwd)
+        self.pending = False
         return [t.clone() for t in self.s_grads]
 
 
@@ -543,6 +566,7 @@ class ClipLoss(nn.Module):
             pull_streams: int = 1,
             exchange: Optional[str] = None,
             cuda_graph: bool = False,
+            compute_dtype: Optional[torch.dtype] = None,
             _kernels=None,
     ):
         super().__init__()
@@ -566,6 +590,11 @@ class ClipLoss(nn.Module):
         if self._exchange not in ("pull", "push"):
             raise ValueError(f"exchange must be 'pull' or 'push', got {self._exchange!r}")
         self._cuda_graph = cuda_graph
+        # None: bf16 inputs run the tcgen05 path, fp32 inputs the exact fp32 path -- except under torch.autocast(bf16),
+        # where fp32 features are cast to bf16 first, as the reference's own matmul is by autocast (train.py amp_bf16)
+        if compute_dtype not in (None, torch.bfloat16, torch.float32):
+            raise ValueError(f"compute_dtype must be None, torch.bfloat16 or torch.float32, got {compute_dtype}")
+        self._compute_dtype = compute_dtype
         self._graphs = {}
         self._kernels = _kernels
         self._comm = None
@@ -606,7 +635,7 @@ class ClipLoss(nn.Module):
             logits_per_text = logit_scale * text_features @ image_features.T
         return logits_per_image, logits_per_text
 
-    def _cfg(self) -> _Cfg:
+    def _cfg(self, will_backward: bool = True, exchange: Optional[str] = None) -> _Cfg:
         k = self._kernels
         if k is None:
             from .kernels import default_kernels
@@ -618,23 +647,42 @@ class ClipLoss(nn.Module):
                 self._comm = _Comm(self.world_size, self.rank, self._group)     # keeps its side stream
             comm = self._comm
         return _Cfg(self.local_loss, self.gather_with_grad, self.rank, self.world_size, k, comm, self._comm_dtype,
-                    self._pipeline, self._symm, self._stream_fwd, self._pull_streams, self._exchange)
+                    self._pipeline, self._symm, self._stream_fwd, self._pull_streams, exchange or self._exchange,
+                    will_backward)
 
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
         if image_features.dim() != 2 or image_features.shape != text_features.shape:
             raise ValueError(f"image_features {tuple(image_features.shape)} and text_features "
                              f"{tuple(text_features.shape)} must both be [batch, dim]")
-        # one compute dtype for both operands: bf16 stays bf16 (tcgen05 path), anything else -> fp32
-        if image_features.dtype == text_features.dtype and image_features.dtype != torch.float16:
-            img, txt = image_features, text_features
-        else:
-            img, txt = image_features.float(), text_features.float()
+        # One compute dtype for both operands: bf16 (tcgen05 path) or fp32 (exact path).  The reference's train loop calls
+        # the loss inside torch.autocast(bf16) on fp32 features (F.normalize is promoted to fp32 by autocast) and its
+        # B x B matmul then runs in bf16: under bf16 autocast -- or with compute_dtype=torch.bfloat16 -- fp32 features
+        # are cast to bf16 here (a differentiable cast: the feature gradients come back in the input dtype).
+        cd = self._compute_dtype
+        if cd is None:
+            both_bf16 = image_features.dtype == torch.bfloat16 and text_features.dtype == torch.bfloat16
+            amp_bf16 = (image_features.is_cuda and torch.is_autocast_enabled("cuda")
+                        and torch.get_autocast_dtype("cuda") == torch.bfloat16)
+            cd = torch.bfloat16 if (both_bf16 or amp_bf16) else torch.float32
+        img = image_features if image_features.dtype == cd else image_features.to(cd)
+        txt = text_features if text_features.dtype == cd else text_features.to(cd)
         img, txt = img.contiguous(), txt.contiguous()
+        will_bwd = torch.is_grad_enabled() and (img.requires_grad or txt.requires_grad or
+                                                (torch.is_tensor(logit_scale) and logit_scale.requires_grad))
         if self._cuda_graph and img.is_cuda and torch.is_grad_enabled():
-            total_loss = self._forward_graphed(img, txt, logit_scale)
+            total_loss = self._forward_graphed(img, txt, logit_scale, will_bwd)
         else:
-            total_loss = _FusedClipLoss.apply(img, txt, logit_scale, self._cfg())
+            total_loss = _FusedClipLoss.apply(img, txt, logit_scale, self._cfg(will_bwd))
         return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+    def graph_input_slots(self, batch: int, dim: int, dtype: torch.dtype = torch.bfloat16):
+        """`cuda_graph=True`: the static (image, text) input tensors of the captured step for [batch, dim] features, or
+        None before that step has been captured.  Features written straight into them (e.g. by
+        `l2_normalize(x, out=slot)`) and passed to `forward` are consumed in place: no per-step input copy."""
+        for key, step in self._graphs.items():
+            if step and key[0] == (batch, dim) and key[1] == dtype:
+                return step.input_slots()
+        return None
 
     def forward_chunks(self, image_chunks, text_chunks, logit_scale, output_dict=False):
         """Gradient-accumulation form of `forward` (src/others/train_other.py:183-191 concatenates cached no-grad
@@ -656,24 +704,48 @@ class ClipLoss(nn.Module):
         total_loss = _ChunkedClipLoss.apply(logit_scale, self._cfg(), len(image_chunks), *chunks)
         return {"contrastive_loss": total_loss} if output_dict else total_loss
 
-    def _forward_graphed(self, img, txt, logit_scale):
+    def _forward_graphed(self, img, txt, logit_scale, will_bwd: bool = True):
         """`cuda_graph=True`: one captured step per (shape, dtype, requires_grad) signature.  All ranks must take
-        the same path (the captured step contains the cross-rank barriers)."""
+        the same path (the captured step contains the cross-rank barriers), so the ranks agree on whether the capture
+        succeeded before anyone uses it."""
         st = torch.is_tensor(logit_scale)
         key = (tuple(img.shape), img.dtype, img.requires_grad, txt.requires_grad, st,
                bool(st and logit_scale.requires_grad), tuple(logit_scale.shape) if st else None)
         step = self._graphs.get(key)
         if step is None:
+            err = None
             try:
-                step = _GraphedStep(img, txt, logit_scale, self._cfg())
+                step = _GraphedStep(img, txt, logit_scale, self._cfg(will_bwd))
             except Exception as e:      # capture refused (e.g. an op that is illegal under capture): stay eager
+                err, step = e, False
+            if self.world_size > 1:
+                ok = torch.tensor([0 if step is False else 1], device=img.device, dtype=torch.int32)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self._group)
+                if int(ok) == 0 and step is not False:
+                    step = False        # another rank failed: nobody replays a step with cross-rank barriers alone
+            if step is False:
                 import warnings
-                warnings.warn(f"xtag_clip_b200: CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly")
-                step = False
+                why = f"{type(err).__name__}: {err}" if err is not None else "capture failed on another rank"
+                warnings.warn(f"xtag_clip_b200: CUDA-graph capture failed ({why}); running eagerly")
             self._graphs[key] = step
         if step is False:
-            return _FusedClipLoss.apply(img, txt, logit_scale, self._cfg())
+            return _FusedClipLoss.apply(img, txt, logit_scale, self._cfg(will_bwd))
+        if step.pending:
+            # a second forward of this signature before the first one's backward: the captured step has ONE set of
+            # saved activations, so this call runs eagerly (pull exchange: it must not touch the peer-writable gather
+            # buffer the pending backward still reads)
+            return _FusedClipLoss.apply(img, txt, logit_scale, self._cfg(will_bwd, exchange="pull"))
         return _GraphedClipLoss.apply(img, txt, logit_scale, step)
+
+    @property
+    def last_path(self):
+        """Diagnostics for benchmarks: which launch / exchange path the module is set up to use."""
+        graphs = [bool(v) for v in self._graphs.values()]
+        ex = None
+        if self._comm is not None:
+            sx = [v for v in self._comm._symm.values() if v is not None]
+            ex = ("symmetric-memory " + ("push" if (sx and sx[0]._pushed) else "pull")) if sx else "nccl"
+        return dict(cuda_graph=bool(graphs) and all(graphs), exchange=ex)
 
 
 def create_loss(args):

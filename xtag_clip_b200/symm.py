@@ -66,6 +66,8 @@ class SymmExchange:
                                       dtype=torch.int64, device=device) for s in range(2)]
         self.s1 = torch.cuda.Stream(device=device)
         self.s2 = torch.cuda.Stream(device=device)
+        self.s3 = torch.cuda.Stream(device=device)      # push exchange: slot-release barrier at the end of a backward
+        self.bwd_pending = False          # push exchange: a forward's gather buffer is still needed by its backward
         self.step = 0
         self.slot = 0
         # streamed forward: per-block ready flags, written by the copy stream right behind each pulled block with the
@@ -173,26 +175,36 @@ class SymmExchange:
             self.h_pflags.barrier(channel=0)                # every rank's flags are zeroed before anyone pushes
         return self.gbuf, self.pflags
 
-    def gather_pushed(self, x: torch.Tensor):
+    def gather_pushed(self, x: torch.Tensor, streams: int = 2):
         """Every rank PUSHES its block into all peers' gather buffers (copy-engine writes over NVLink, ring order
         r+1, r+2, ...) and writes the step's epoch into the peer's ready flag behind it.  The consumer is the
         flag-gated persistent K1 launch, so no barrier is needed before the exchange: a rank that is late only delays
         its own block at its peers (the pull exchange pays the start-of-step barrier skew, measured 68 us at 8 GPUs).
-        Buffers are double-buffered by step parity; a rank can only be two steps ahead of a peer after passing the
-        previous step's column-LSE barrier, by which time that peer has finished reading the slot.
-        Returns (gather buffer [B, D] of this step, order, wait, flags [W])."""
+        streams = 2: the blocks alternate between two copy streams, so one stream's flag copy and scheduling gaps
+        (11 us per block, measured) hide behind the other stream's 17 us block copy -- the blocks then arrive faster
+        than K1 consumes them (one [b, B/W] column block of config 5 is ~19 us of tensor time).
+        Slot safety: the previous backward ended with a release barrier on s3 (`push_step_done`): no peer still reads
+        the slot this step's pushes overwrite.  Returns (gather buffer [B, D] of this step, order, wait, flags [W])."""
         gbuf, pflags = self._push_buffers()
         b, s, W, r = self.b, self.slot, self.W, self.r
         cur = torch.cuda.current_stream()
         self.epoch.add_(1)
         gbuf[s][r * b:(r + 1) * b].copy_(x)
         self.s1.wait_stream(cur)
-        with torch.cuda.stream(self.s1):
-            for j in range(1, W):
-                p = (r + j) % W
+        if not torch.cuda.is_current_stream_capturing():    # (a captured backward joins s3 itself before it ends)
+            self.s1.wait_stream(self.s3)                    # release barrier of the previous backward
+        sts = [self.s1]
+        if streams >= 2 and W > 2:
+            ready = torch.cuda.Event()
+            ready.record(self.s1)
+            self.s2.wait_event(ready)
+            sts.append(self.s2)
+        for j in range(1, W):
+            p = (r + j) % W
+            with torch.cuda.stream(sts[(j - 1) % len(sts)]):
                 self.peer_gbuf[p][s][r * b:(r + 1) * b].copy_(x, non_blocking=True)
                 self.peer_pflags[p][s][r:r + 1].copy_(self.epoch, non_blocking=True)
-        self._streamed_two = False
+        self._streamed_two = len(sts) == 2
         self._pushed = True
         # the block of rank q is q's ((r - q) % W)-th push: r-1 lands first, then r-2, ...
         order = [(r - j) % W for j in range(W)]
@@ -201,9 +213,16 @@ class SymmExchange:
     def push_step_done(self):
         """End of a backward in push mode: no rank may start pushing the next step's blocks into a peer's gather buffer
         while that peer's gradient GEMMs still read it.  Eager steps alternate between two slots and would be safe
-        without this, but a captured step replays ONE slot; the barrier sits right behind the reduce-scatter barrier
-        of the same backward, so the ranks arrive within a few microseconds of each other."""
-        self.h_gbuf.barrier(channel=1)
+        without this, but a captured step replays ONE slot.  The barrier runs on its own stream behind everything the
+        backward has enqueued so far; only the next step's pushes wait for it (`gather_pushed`), not the compute stream
+        -- except under stream capture, where every forked stream must be joined before the capture ends."""
+        cur = torch.cuda.current_stream()
+        self.s3.wait_stream(cur)
+        with torch.cuda.stream(self.s3):
+            self.h_gbuf.barrier(channel=1)
+        if torch.cuda.is_current_stream_capturing():
+            cur.wait_stream(self.s3)
+        self.bwd_pending = False
 
     def end_gather(self, streamed: bool = False):
         """the pull streams must be drained before the next barrier on s1 (orders the next overwrite of a slot).
