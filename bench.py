@@ -32,7 +32,7 @@ UNIT = "samples/s"
 GLOBAL_BATCH = 32768
 DIM = 1024
 LOGIT_SCALE = 14.285714          # exp(2.659), the reference's init (model.py:263)
-CPU_SAMPLE_B = 4096              # bounded CPU sample: the C5 shape at 1/8 of the batch
+CPU_SHARDS = 8                   # bounded CPU sample: 1 of 8 row shards of the whole-batch problem
 
 
 def _peaks():
@@ -55,61 +55,108 @@ def _synth(rank: int, b: int, d: int, device, dtype):
 
 
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference_step_time(B: int, D: int, iters: int = 5, warmup: int = 2):
-    """The reference's own algorithm for this path on the host cores: oracle/clip_oracle.py (a restatement of
-    src/open_clip/loss.py:104-139; the Python reference itself cannot travel to the GPU box), fp32, all threads."""
+def workload_config(B: int, D: int, world: int):
+    """`config` of the JSON line: names the workload only, so both arms (ours / --impl reference) print the same."""
+    b = B // world
+    return dict(workload=f"C5: ViT-H-14 contrastive head (ClipLoss fwd+bwd), global batch {B}, dim {D}",
+                global_batch=B, dim=D, per_rank_batch=b,
+                parallelism=f"dp{world} (rows sharded, local_loss + gather_with_grad)" if world > 1 else "dp1",
+                l2=f"no flush: per-step working set (features + {b}x{B} logit-sized matrices) = "
+                   f"{(2 * b * B * 2 * 2 + 4 * B * D * 2) / 2**20:.0f} MiB > 126 MB L2")
+
+
+def cpu_shard_step_time(B: int, D: int, shards: int, iters: int, warmup: int):
+    """The reference's algorithm on the host cores, bounded: ONE of `shards` row shards of the whole-batch problem --
+    rows [0, B/shards) of both B x B logit matrices against all B columns, forward + backward, exactly what one rank of
+    the reference's local_loss world computes (oracle.clip_loss_local_rank restates loss.py:95-96, 116-118, 134-137;
+    the Python reference cannot travel to the GPU box).  The shards partition the rows, so a whole-batch step is
+    `shards` such steps: no B^2 extrapolation.  fp32, every host thread."""
     import torch
     import oracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     I, T = _synth(0, B, D, "cpu", torch.float32)
-    I.requires_grad_(True)
-    T.requires_grad_(True)
+    b = B // shards
+    Il = I[:b].clone().requires_grad_(True)
+    Tl = T[:b].clone().requires_grad_(True)
     s = torch.tensor(LOGIT_SCALE, requires_grad=True)
-    best = float("inf")
+    times = []
     for it in range(warmup + iters):
-        I.grad = T.grad = s.grad = None
+        Il.grad = Tl.grad = s.grad = None
         t0 = time.perf_counter()
-        loss = oracle.clip_loss_single(I, T, s)
+        loss = oracle.clip_loss_local_rank(Il, Tl, I, T, s, 0)
         loss.backward()
         dt = time.perf_counter() - t0
         if it >= warmup:
-            best = min(best, dt)
-    return best, cores
+            times.append(dt)
+    return times, cores, float(loss)
 
 
-def cpu_baseline_record(full_B: int):
-    t, cores = cpu_reference_step_time(CPU_SAMPLE_B, DIM)
-    raw = CPU_SAMPLE_B / t
-    # per-step cost of this path is proportional to B^2 (B x B logits), so samples/s at the full batch is
-    # raw * (B_sample / B_full)
-    value = raw * CPU_SAMPLE_B / full_B
-    return dict(value=value, unit=UNIT, cores=cores, kind="port",
-                sample=f"oracle ClipLoss fwd+bwd fp32, B={CPU_SAMPLE_B} D={DIM}, best of 5: {t * 1e3:.1f} ms/step "
-                       f"= {raw:.0f} samples/s at B={CPU_SAMPLE_B}; scaled by B_sample/B_full (cost ~ B^2) to "
-                       f"global batch {full_B}")
+def cpu_full_step_time(B: int, D: int):
+    """ONE real whole-batch step of the reference's W=1 path (oracle.clip_loss_single: two B x B logit matrices) when
+    the host has the memory for it (~12 B x B fp32 matrices live at the peak); None otherwise."""
+    import torch
+    import oracle
+    try:
+        import psutil
+        if psutil.virtual_memory().available < 14 * B * B * 4:
+            return None
+    except Exception:
+        return None
+    I, T = _synth(0, B, D, "cpu", torch.float32)
+    I.requires_grad_(True)
+    T.requires_grad_(True)
+    s = torch.tensor(LOGIT_SCALE, requires_grad=True)
+    t0 = time.perf_counter()
+    oracle.clip_loss_single(I, T, s).backward()
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_record(full_B: int, D: int, full_step: bool):
+    times, cores, _ = cpu_shard_step_time(full_B, D, CPU_SHARDS, iters=3, warmup=1)
+    t = statistics.median(times)
+    value = full_B / (CPU_SHARDS * t)
+    rec = dict(value=value, unit=UNIT, cores=cores, kind="port",
+               sample=f"oracle port of the reference ClipLoss (fp32, torch CPU, {cores} threads): rows [0, {full_B // CPU_SHARDS})"
+                      f" of both {full_B} x {full_B} logit matrices (1 of {CPU_SHARDS} row shards of the whole-batch step = one "
+                      f"rank of the reference's local_loss world), fwd+bwd, median of 3: {t * 1e3:.0f} ms; whole-batch step = "
+                      f"{CPU_SHARDS} shards = {CPU_SHARDS * t * 1e3:.0f} ms")
+    if full_step:
+        try:
+            tf = cpu_full_step_time(full_B, D)
+        except Exception as e:          # e.g. the host ran out of memory after all
+            tf = None
+            rec["full_batch_step_error"] = f"{type(e).__name__}: {e}"[:200]
+        if tf is not None:
+            rec["measured_full_batch_step_ms"] = tf * 1e3
+            rec["measured_full_batch_samples_per_s"] = full_B / tf
+    return rec
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port: the reference is Python
+    and /root/reference does not exist on the GPU box) on this arm's config, metric and unit.  A step is one bounded
+    sample of the workload (one of 8 row shards, see cpu_shard_step_time); rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     K, W = args.steps, args.warmup
-    t, cores = cpu_reference_step_time(CPU_SAMPLE_B, DIM, iters=max(K, 1), warmup=max(W, 1))
-    raw = CPU_SAMPLE_B / t
-    value = raw * CPU_SAMPLE_B / GLOBAL_BATCH
-    ms_full = t * 1e3 * (GLOBAL_BATCH / CPU_SAMPLE_B) ** 2
-    sample = (f"oracle port of the reference ClipLoss (fp32, torch CPU, {cores} threads): each step is fwd+bwd at "
-              f"B={CPU_SAMPLE_B}, D={DIM} ({t * 1e3:.1f} ms, {raw:.0f} samples/s); value is scaled to the global batch "
-              f"{GLOBAL_BATCH} by B_sample/B_full because the step cost grows as B^2")
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=K, warmup=W, ms_per_step=ms_full,
-                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
-                impl="reference",
-                config=dict(workload="C5: ViT-H-14 contrastive head, global batch 32768, dim 1024 (CPU: bounded sample)",
-                            global_batch=GLOBAL_BATCH, dim=DIM),
+    B, D = args.batch, args.dim
+    times, cores, loss = cpu_shard_step_time(B, D, CPU_SHARDS, iters=max(K, 1), warmup=max(W, 1))
+    t = sum(times) / len(times)
+    value = B / (CPU_SHARDS * t)
+    sample = (f"oracle port of the reference ClipLoss (fp32, torch CPU, {cores} threads): each step is fwd+bwd of rows "
+              f"[0, {B // CPU_SHARDS}) of both {B} x {B} logit matrices against all {B} columns -- 1 of {CPU_SHARDS} row "
+              f"shards of the whole-batch step, what one rank of the reference's local_loss world computes "
+              f"({t * 1e3:.0f} ms mean of {len(times)}); ms_per_step and value are for the whole batch = {CPU_SHARDS} "
+              f"shards (the shards partition the rows exactly)")
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=K, warmup=W,
+                ms_per_step=CPU_SHARDS * t * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=workload_config(B, D, max(args.gpus, 1)),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                gpu_launches=0)
+                gpu_launches=0, loss_of_sample=loss)
     print(json.dumps(line), flush=True)
 
 
@@ -180,6 +227,164 @@ class ClockSampler:
                     samples=len(sm), power_w_max=max(power))
 
 
+def _bind_to_gpu_numa_node(local_rank: int):
+    """Pin this process to the CPUs of the GPU's NUMA node BEFORE any pinned host memory is allocated: with 8 ranks
+    on one host the per-step H2D copies otherwise cross the socket interconnect.  Best effort."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        bdf = f"{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return dict(numa_node=node, cpus=len(allowed))
+    except Exception:
+        return None
+    return None
+
+
+def _ncu_traffic(kernel_sig: str):
+    """DRAM bytes (read + write) per launch of the kernel whose name contains `kernel_sig`, from the newest committed
+    `ncu --set full` raw page under profiles/ (1 GPU, config 5).  -> (bytes | None, file | None)"""
+    import csv
+    import glob
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full*raw.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(f)))
+            hdr, units = rows[0], rows[1]
+            kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            vals = [float(r[rd]) * mult[units[rd]] + float(r[wr]) * mult[units[wr]]
+                    for r in rows[2:] if len(r) > max(rd, wr) and kernel_sig in r[kn]]
+            if vals:
+                return sum(vals) / len(vals), os.path.relpath(f, ROOT)
+        except Exception:
+            continue
+    return None, None
+
+
+def _time_steps(fn, iters, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def torch_b200_record(I_dev, T_dev, log_scale):
+    """Stock PyTorch on the SAME GPU in the SAME run: the reference's ClipLoss expressions (loss.py:116-137: two
+    logit GEMMs, F.cross_entropy on each) under torch.autocast(bf16), eager -- the number the kernels have to beat."""
+    import torch
+    import torch.nn.functional as F
+    B = I_dev.shape[0]
+    labels = torch.arange(B, device=I_dev.device)
+
+    def step():
+        I_dev.grad = T_dev.grad = log_scale.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            s = log_scale.exp()
+            li = s * I_dev @ T_dev.T
+            lt = s * T_dev @ I_dev.T
+            loss = (F.cross_entropy(li, labels) + F.cross_entropy(lt, labels)) / 2
+        loss.backward()
+        return loss
+
+    try:
+        ms = _time_steps(step, iters=5, warmup=2)
+        return dict(ms_per_step=ms, value=B / ms * 1e3, unit=UNIT, loss=float(step()),
+                    what="stock torch eager ClipLoss math under bf16 autocast, same GPU, same inputs")
+    except Exception as e:
+        return dict(error=f"{type(e).__name__}: {e}"[:200])
+    finally:
+        I_dev.grad = T_dev.grad = log_scale.grad = None
+        torch.cuda.empty_cache()
+
+
+def config_subrecords(dev, world, rank):
+    """The other BASELINE configs as sub-records (1 GPU: C2 sweep and the C3 tag head; N > 1: C4 at this world size)."""
+    import torch
+    import torch.distributed as dist
+    import xtag_clip_b200 as xt
+    out = {}
+    if world == 1:
+        c2 = []
+        for B in (256, 512, 1024, 2048, 4096):
+            I, T = _synth(0, B, 512, "cpu", torch.bfloat16)
+            I = I.to(dev).requires_grad_(True)
+            T = T.to(dev).requires_grad_(True)
+            ls = torch.tensor(2.659260036932778, device=dev, requires_grad=True)
+            rec = dict(B=B, D=512)
+            for name, mod in (("graph", xt.ClipLoss(cuda_graph=True)), ("eager", xt.ClipLoss())):
+                def step():
+                    I.grad = T.grad = ls.grad = None
+                    mod(I, T, ls.exp()).backward()
+                ms = _time_steps(step, iters=50, warmup=5)
+                rec[f"{name}_ms"] = ms
+            rec["samples_per_s"] = B / min(rec["graph_ms"], rec["eager_ms"]) * 1e3
+            c2.append(rec)
+        out["C2_vit_b32_head_sweep_bf16"] = c2
+        try:
+            b, N, D = 1024, 197, 512
+            head = xt.TagHead(D).to(dev).train()
+            asl = xt.AsymmetricLoss(gamma_neg=4, gamma_pos=1, clip=0.05)
+            tok = torch.randn(b, N, D, device=dev, dtype=torch.bfloat16, requires_grad=True)
+            y = (torch.rand(b, 22, device=dev) > 0.7).float().repeat(1, 2)
+
+            def step_head():
+                tok.grad = None
+                head.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    logits = head.tag_forward(tok)
+                asl(logits.float(), y).backward()
+
+            ms = _time_steps(step_head, iters=10, warmup=3)
+            out["C3_tag_head_fwd_bwd_train_bf16"] = dict(b=b, N=N, D=D, ms_per_step=ms, samples_per_s=b / ms * 1e3,
+                                                         what="TagHead.tag_forward (2 cross-attention layers, dropout 0.1)"
+                                                              " + AsymmetricLoss, fwd+bwd, bf16 autocast")
+        except Exception as e:
+            out["C3_tag_head_fwd_bwd_train_bf16"] = dict(error=f"{type(e).__name__}: {e}"[:200])
+    else:
+        B, D = 8192, 768
+        b = B // world
+        I, T = _synth(rank, b, D, "cpu", torch.bfloat16)
+        I = I.to(dev).requires_grad_(True)
+        T = T.to(dev).requires_grad_(True)
+        ls = torch.tensor(2.659260036932778, device=dev, requires_grad=True)
+        mod = xt.ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world, cuda_graph=True)
+
+        def step():
+            I.grad = T.grad = ls.grad = None
+            mod(I, T, ls.exp()).backward()
+
+        for _ in range(5):
+            step()
+        dist.barrier()
+        ms = _time_steps(step, iters=50, warmup=3)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+        out["C4_vit_l16_global8192_d768"] = dict(B=B, D=D, world=world, per_rank_batch=b, ms_per_step=ms,
+                                                 samples_per_s=B / ms * 1e3,
+                                                 algorithmic_tflops_per_gpu=6.0 * B * B * D / world / (ms * 1e-3) / 1e12,
+                                                 path=mod.last_path)
+    return out
+
+
 def run_ours(args):
     from xtag_clip_b200._cuda_probe import wait_for_cuda
     wait_for_cuda()
@@ -197,6 +402,7 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = _bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, D = args.batch, args.dim
@@ -215,7 +421,7 @@ def run_ours(args):
                            world_size=world, cuda_graph=not args.no_graph, pull_streams=args.pull_streams,
                            exchange=args.exchange)
     loss_eager = xt.ClipLoss(local_loss=world > 1, gather_with_grad=world > 1, cache_labels=True, rank=rank,
-                             world_size=world)
+                             world_size=world, pull_streams=args.pull_streams, exchange=args.exchange)
 
     def step(I, T, mod=None):
         I.grad = T.grad = log_scale.grad = None
@@ -235,6 +441,13 @@ def run_ours(args):
     for _ in range(W):
         loss = step(I_dev, T_dev)
     barrier()
+    # the fast path must be the one that is timed: a silent degradation (graph capture refused -> eager launches,
+    # symmetric memory unavailable -> NCCL P2P) would still print a number
+    path = loss_mod.last_path
+    if not args.no_graph and not path["cuda_graph"]:
+        raise SystemExit(f"bench.py: CUDA-graph capture fell back to eager launches ({path}); refusing to time it")
+    if world > 1 and not str(path["exchange"]).startswith("symmetric-memory"):
+        raise SystemExit(f"bench.py: the symmetric-memory exchange fell back to {path['exchange']}; refusing to time it")
 
     # ---- device-resident leg (value) ----
     n0 = _lib.launch_count()
@@ -249,17 +462,21 @@ def run_ours(args):
     t_hi = time.time()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - n0
-    # a timed region shorter than the 200 ms sampling period yields no clock sample: keep the SAME steps running
-    # (untimed, on every rank -- the steps contain collectives) until a few samples under this exact load exist
+    # Sustained window: the SAME steps for >= 1.2 s more (on every rank -- the steps contain collectives).  It yields
+    # the clock samples of this exact load (the timed region above can be shorter than the 200 ms sampling period)
+    # and a second throughput figure taken in the settled power state, comparable between N = 1 and N = 8.
     ms_max = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms_max, op=dist.ReduceOp.MAX)
-    if float(ms_max) < 600.0:
-        extra = int(800.0 / max(float(ms_max) / K, 1e-3)) + 1
-        for _ in range(extra):
-            step(I_dev, T_dev)
-        barrier()
-        t_hi = time.time()
+    n_sus = int(1200.0 / max(float(ms_max) / K, 1e-3)) + 1
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(n_sus):
+        step(I_dev, T_dev)
+    s1.record()
+    barrier()
+    t_hi = time.time()
+    ms_sus = s0.elapsed_time(s1)
     clocks = sampler.stop(t_lo, t_hi) if sampler else None
     loss_val = float(loss.item())
 
@@ -316,6 +533,15 @@ def run_ours(args):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    # what the H2D copies alone cost when every rank copies at once (diagnostic for the e2e figure at N > 1)
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(copy_stream)
+    for i in range(10):
+        h2d(i & 1)
+    g1.record(copy_stream)
+    barrier()
+    ms_h2d = g0.elapsed_time(g1) / 10
 
     # ---- per-kernel pass for the roofline (CUDA events recorded inside the library on the launch stream) ----
     # (eager module: the library's per-launch events are recorded at launch time, a graph replay launches nothing
@@ -336,13 +562,23 @@ def run_ours(args):
     per = {}
     for i in range(n):
         per.setdefault(tags[i], []).append((tms[i], work[i]))
+    barrier()
 
-    t_ms = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    t_ms = torch.tensor([ms, ms_e2e, ms_sus, ms_h2d], device=dev, dtype=torch.float64)
     l_cnt = torch.tensor([launches], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(l_cnt, op=dist.ReduceOp.SUM)
-    ms, ms_e2e = float(t_ms[0]), float(t_ms[1])
+    ms, ms_e2e, ms_sus, ms_h2d = (float(x) for x in t_ms)
+
+    extra = {}
+    if not args.no_extras:
+        try:
+            extra = config_subrecords(dev, world, rank)
+        except Exception as e:
+            extra = dict(error=f"{type(e).__name__}: {e}"[:300])
+        if world == 1:
+            extra["torch_b200"] = torch_b200_record(I_dev, T_dev, log_scale)
 
     if rank == 0:
         peaks = _peaks()
@@ -350,48 +586,63 @@ def run_ours(args):
         e2e_value = B * K / (ms_e2e * 1e-3)
         names = {0: "tc_gemm_kernel<EPI_LSE> (K1 fused forward)", 1: "tc_gemm_kernel<EPI_DS> (K2 dS producer)",
                  2: "tc_gemm_kernel<EPI_STORE> (K2 dI/dT GEMM)"}
+        sigs = {0: "tc_gemm_kernel<0,", 1: "tc_gemm_kernel<1,", 2: "tc_gemm_kernel<2,"}
         kern = {}
         for tag, recs in per.items():
             tot_ms = sum(r[0] for r in recs)
             tot_w = sum(r[1] for r in recs)
+            tf = tot_w / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else None
             kern[names.get(tag, str(tag))] = dict(launches_per_step=len(recs) / K, avg_ms=tot_ms / len(recs),
-                                                  share_of_step=tot_ms / K / (ms / K),
-                                                  tflops=tot_w / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else None)
-        dom_tag = max(per, key=lambda t: sum(r[0] for r in per[t])) if per else None
-        roofline = None
-        if dom_tag is not None:
-            recs = per[dom_tag]
+                                                  share_of_step=tot_ms / K / (ms / K), tflops=tf,
+                                                  frac_of_sustained_peak=tf / peaks["sustained"] if tf else None,
+                                                  frac_of_burst_peak=tf / peaks["burst"] if tf else None)
+
+        def roof(tag):
+            recs = per[tag]
             ach = sum(r[1] for r in recs) / (sum(r[0] for r in recs) * 1e-3) / 1e12
-            # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (1 GPU, this config)
-            traffic = 3.32e9 if (dom_tag == 2 and world == 1 and B == GLOBAL_BATCH and D == DIM) else None
-            roofline = dict(bound="tensor", kernel=names.get(dom_tag), achieved=ach, peak=peaks["sustained"],
-                            unit="TFLOP/s", frac=ach / peaks["sustained"], traffic=traffic,
-                            traffic_src="profiles/r1_ncu_full_final_raw.csv (dram__bytes_read+write per launch; "
-                                        "algorithmic 2.27e9)" if traffic else None,
-                            peak_kind=f"bf16 sustained, {peaks['src']} (kernel timed inside a long step); "
-                                      f"burst peak {peaks['burst']}",
-                            flops_per_launch=sum(r[1] for r in recs) / len(recs),
-                            avg_launch_ms=sum(r[0] for r in recs) / len(recs))
+            traffic, src = _ncu_traffic(sigs.get(tag, "?")) if (world == 1 and B == GLOBAL_BATCH and D == DIM) else (None, None)
+            return dict(bound="tensor", kernel=names.get(tag), achieved=ach, peak=peaks["sustained"], unit="TFLOP/s",
+                        frac=ach / peaks["sustained"], frac_of_burst_peak=ach / peaks["burst"], traffic=traffic,
+                        traffic_src=f"{src}: dram__bytes_read.sum + dram__bytes_write.sum per launch" if src else None,
+                        peak_kind=f"bf16 sustained, {peaks['src']} (kernel timed inside a long step); burst peak "
+                                  f"{peaks['burst']}",
+                        flops_per_launch=sum(r[1] for r in recs) / len(recs),
+                        avg_launch_ms=sum(r[0] for r in recs) / len(recs))
+
+        roofline = roofline_longest = None
+        if per:
+            dom_tag = max(per, key=lambda t: sum(r[0] for r in per[t]))                 # largest share of the step
+            long_tag = max(per, key=lambda t: sum(r[0] for r in per[t]) / len(per[t]))  # longest single launch
+            roofline = roof(dom_tag)
+            roofline_longest = roof(long_tag)
         step_tflops_per_gpu = 6.0 * B * B * D / world / (ms / K * 1e-3) / 1e12
-        cpu = cpu_baseline_record(B) if world == 1 and not args.no_cpu else None
+        sus_tflops_per_gpu = 6.0 * B * B * D / world / (ms_sus / n_sus * 1e-3) / 1e12
+        cpu = cpu_baseline_record(B, D, full_step=not args.no_cpu_full) if world == 1 and not args.no_cpu else None
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
                     higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16", data="synthetic",
-                    config=dict(workload=f"C5: ViT-H-14 contrastive head (ClipLoss fwd+bwd), global batch {B}, dim {D}, "
-                                         f"{'local_loss+gather_with_grad, ' if world > 1 else ''}bf16",
-                                global_batch=B, dim=D, per_rank_batch=b, parallelism=f"dp{world} (rows sharded)",
-                                launch="eager" if args.no_graph else "CUDA-graph replay (ClipLoss(cuda_graph=True))",
-                                l2=f"no flush: per-step working set (features + {b}x{B} bf16 dS x2) = "
-                                   f"{(2 * b * B * 2 * 2 + 4 * B * D * 2) / 2**20:.0f} MiB > 126 MB L2"),
+                    config=workload_config(B, D, world),
+                    run=dict(launch="eager" if args.no_graph else "CUDA-graph replay (ClipLoss(cuda_graph=True))",
+                             path=path, numa=numa,
+                             exchange=None if world == 1 else
+                             "feature all-gather, column-LSE combine and dT reduce-scatter by copy engines / kernels over "
+                             "peer-mapped symmetric memory (torch.distributed._symmetric_memory); the NCCL process group "
+                             "only carries the rendezvous and bench.py's barriers"),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=2 * b * D * 2 * world,
-                             d2h_bytes_per_step=4 * world, ms_per_step=ms_e2e / K),
+                             d2h_bytes_per_step=4 * world, ms_per_step=ms_e2e / K, h2d_only_ms_per_step=ms_h2d),
                     gpu_launches=int(l_cnt[0]),
-                    roofline=roofline,
+                    roofline=roofline, roofline_longest_launch=roofline_longest,
                     tensor_frac_of_step=dict(algorithmic_tflops_per_gpu=step_tflops_per_gpu,
                                              frac_of_burst_peak=step_tflops_per_gpu / peaks["burst"],
                                              frac_of_sustained_peak=step_tflops_per_gpu / peaks["sustained"],
                                              note="6*B^2*D / (W * t_step); backward recompute not credited"),
-                    kernels=kern, loss=loss_val)
+                    sustained=dict(steps=n_sus, window_s=ms_sus * 1e-3, ms_per_step=ms_sus / n_sus,
+                                   value=B * n_sus / (ms_sus * 1e-3), unit=UNIT,
+                                   algorithmic_tflops_per_gpu=sus_tflops_per_gpu,
+                                   frac_of_burst_peak=sus_tflops_per_gpu / peaks["burst"],
+                                   frac_of_sustained_peak=sus_tflops_per_gpu / peaks["sustained"],
+                                   note="same steps, run back to back for >= 1.2 s right after the timed region"),
+                    kernels=kern, loss=loss_val, **({"configs": extra} if extra else {}))
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -409,6 +660,8 @@ def main():
     ap.add_argument("--batch", type=int, default=GLOBAL_BATCH, help="global batch (default: BASELINE config 5)")
     ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-cpu-full", action="store_true", help="skip the one real whole-batch CPU step of cpu_baseline")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C2 / C3 / C4 / torch_b200 sub-records")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--pull-streams", type=int, default=2,
                     help="copy streams of the streamed feature exchange (see symm.gather_streamed / gather_pushed)")

@@ -19,6 +19,7 @@ from .clip_oracle import (  # noqa: F401
     clip_loss_single,
     clip_loss_world,
     clip_loss_closed_form,
+    clip_loss_local_rank,
 )
 from .tag_oracle import (  # noqa: F401
     TAG_CFG,

@@ -169,3 +169,15 @@ def clip_loss_world(
             if leaf_T[k].grad is not None:
                 dT[k] = dT[k] + leaf_T[k].grad
     return losses, dI, dT, dS
+
+
+def clip_loss_local_rank(I_loc, T_loc, all_I, all_T, logit_scale, rank: int) -> torch.Tensor:
+    """What ONE rank of a ``local_loss`` world computes (loss.py:116-118 logits, :95-96 labels, :134-137 loss):
+    its b rows of both logit matrices against all B gathered columns.  The W rank shards partition the rows of the
+    two B x B matrices exactly, so W such steps are the whole-batch work of the reference's algorithm (bench.py times
+    this as the bounded CPU sample of config 5)."""
+    li = (logit_scale * I_loc) @ all_T.T
+    lt = (logit_scale * T_loc) @ all_I.T
+    n = li.shape[0]
+    labels = torch.arange(n, dtype=torch.long) + n * rank
+    return (_ce_mean(li, labels) + _ce_mean(lt, labels)) / 2
