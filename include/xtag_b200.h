@@ -125,6 +125,9 @@ int xtag_clip_fwd_block(const void* A, const void* Bm_blk, int dtype, int M, int
                         const float* scale, int label_offset,
                         float* row_part, float* col_part, int col_ld, float* diag, void* stream);
 int xtag_lse_reduce_log2(const float* parts, int P, int n, float* out, void* stream);
+/* two such reductions (the row and the column partials of one forward) in ONE launch */
+int xtag_lse_reduce2_log2(const float* parts0, int P0, int n0, float* out0,
+                          const float* parts1, int P1, int n1, float* out1, void* stream);
 
 /* K1 fused with the feature exchange: ONE persistent launch over the whole gather buffer Bm_all [N, D] whose nblk
  * column blocks (blk_cols rows each, a multiple of 256) are filled concurrently by copy-engine pulls from the peers.
@@ -149,6 +152,11 @@ int xtag_lse_combine(const float* parts, int W, int N, float* out, void* stream)
  *   xtag_sum_ptrs_bf16    : out[i] = sum_w parts[w][i], n bf16 elements    (reduce step of the pull-based
  *                                                                           reduce-scatter of the text gradient) */
 int xtag_lse_combine_ptrs(const float* const* parts_dev, int W, int N, float* out, void* stream);
+/* xtag_lse_combine_ptrs + xtag_clip_loss (+ the epoch bump of the flag-gated forward) in one launch: col_out [N] =
+ * combined column LSEs; loss_out[0] = this rank's loss over its M rows / label columns [label_offset, label_offset+M);
+ * epoch (device int, may be NULL) is incremented once, for the next forward. */
+int xtag_lse_combine_ptrs_loss(const float* const* parts_dev, int W, int N, float* col_out, const float* row_lse,
+                               const float* diag, int M, int label_offset, float* loss_out, int* epoch, void* stream);
 int xtag_sum_ptrs_bf16(const void* const* parts_dev, int W, size_t n, void* out, void* stream);
 
 /* loss = 0.5 * [ mean_i(row_lse_i - diag_i) + mean_i(col_lse[label_offset+i] - diag_i) ]

@@ -187,7 +187,7 @@ def test_launch_counter_counts_native_kernels():
     n0 = _lib.launch_count()
     I, T = feats(1, 256, 512)
     xt.ClipLoss()(I.bfloat16().cuda(), T.bfloat16().cuda(), 10.0)
-    assert _lib.launch_count() - n0 >= 4          # tcgen05 fwd + 2 reductions + loss
+    assert _lib.launch_count() - n0 >= 3          # tcgen05 fwd + fused row/column reduction + loss
 
 
 def test_cliploss_cuda_graph_replay_matches_eager():

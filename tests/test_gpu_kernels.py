@@ -448,3 +448,34 @@ def test_asl_golden(K, golden_dir):
         assert rel_err(dx, g[f"k{n}_dx"]) < 1e-5
         ref_idx = oracle.control_word_indices(torch.from_numpy(g["x"]))
         assert torch.equal(idx.cpu().long(), ref_idx)
+
+
+def test_lse_reduce2_and_combine_loss(K):
+    """The fused small kernels of the sharded forward: two log2-domain reductions in one launch, and the column-LSE
+    combine over W buffers + the rank's loss + the epoch bump in one launch, against torch."""
+    g = torch.Generator().manual_seed(3)
+    p0 = (torch.randn(37, 1000, generator=g) * 30).cuda()
+    p0[5, 10] = float("-inf")
+    p0[:, 11] = float("-inf")
+    p1 = (torch.randn(256, 333, generator=g) * 5).cuda()
+    o0 = torch.empty(1000, device="cuda")
+    o1 = torch.empty(333, device="cuda")
+    from xtag_clip_b200._lib import check
+    check(K.lib.xtag_lse_reduce2_log2(p0.data_ptr(), 37, 1000, o0.data_ptr(), p1.data_ptr(), 256, 333, o1.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream), "reduce2")
+    ln2 = 0.6931471805599453
+    r0 = torch.logsumexp(p0.double() * ln2, dim=0)
+    r1 = torch.logsumexp(p1.double() * ln2, dim=0)
+    assert torch.isneginf(o0[11]) and rel_err(o0[torch.isfinite(r0)], r0[torch.isfinite(r0)]) < 1e-6
+    assert rel_err(o1, r1) < 1e-6
+    W, N, M, off = 5, 4096, 512, 1024
+    parts = [(torch.randn(N, generator=g) * 8).cuda() for _ in range(W)]
+    ptrs = torch.tensor([t.data_ptr() for t in parts], dtype=torch.int64, device="cuda")
+    row = torch.randn(M, generator=g).cuda() * 3 + 9
+    diag = torch.randn(M, generator=g).cuda()
+    epoch = torch.tensor([41], dtype=torch.int32, device="cuda")
+    col, loss = K.lse_combine_ptrs_loss(ptrs, W, N, row, diag, off, epoch)
+    cref = torch.logsumexp(torch.stack(parts).double(), dim=0)
+    lref = 0.5 * (row.double() + cref[off:off + M] - 2 * diag.double()).mean()
+    assert rel_err(col, cref) < 1e-6 and abs(float(loss) - float(lref)) < 1e-5 * abs(float(lref)) and int(epoch) == 42
+    assert rel_err(K.lse_combine_ptrs(ptrs, W, N), cref) < 1e-6

@@ -130,6 +130,59 @@ __global__ void __launch_bounds__(256) lse_reduce_kernel(const float* __restrict
   }
 }
 
+// Two independent reductions of log2-domain partials in ONE launch (the row and the column partials a K1 launch leaves
+// behind): blocks [0, nb0) work on problem 0, the rest on problem 1.  512 threads = 32 consecutive outputs x 16 groups
+// of parts; every thread first takes the maximum of its parts and then sums the exponentials, both with independent
+// (unrolled) loads, instead of the serial online update of lse_reduce_kernel: the row reduction of a sharded forward
+// (256 partials per row, 4096 rows) drops from 15 us to a few.
+struct Reduce2 {
+  const float* parts[2];
+  float* out[2];
+  int P[2], n[2], nb0;
+};
+__global__ void __launch_bounds__(512) lse_reduce2_kernel(const __grid_constant__ Reduce2 r) {
+  __shared__ float sm_m[16][33], sm_l[16][33];
+  const int which = ((int)blockIdx.x >= r.nb0) ? 1 : 0;
+  const int blk = which ? (int)blockIdx.x - r.nb0 : (int)blockIdx.x;
+  const float* __restrict__ parts = r.parts[which];
+  const int P = r.P[which], n = r.n[which];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blk * 32 + tx;
+  float m = -INFINITY, l = 0.f;
+  if (i < n) {
+    for (int p0 = ty; p0 < P; p0 += 16 * 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int p = p0 + u * 16;
+        v[u] = (p < P) ? parts[(size_t)p * n + i] : -INFINITY;
+      }
+      float mx = m;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) mx = fmaxf(mx, v[u]);
+      if (mx > -INFINITY) {
+        float acc = (m > -INFINITY) ? l * exp2f(m - mx) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += exp2f(v[u] - mx);     // exp2f(-inf) == 0
+        l = acc;
+        m = mx;
+      }
+    }
+  }
+  sm_m[ty][tx] = m;
+  sm_l[ty][tx] = l;
+  __syncthreads();
+  if (ty == 0 && i < n) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) mx = fmaxf(mx, sm_m[g][tx]);
+    float tot = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) tot += (sm_m[g][tx] > -INFINITY) ? sm_l[g][tx] * exp2f(sm_m[g][tx] - mx) : 0.f;
+    r.out[which][i] = (mx + log2f(tot)) * kLn2;
+  }
+}
+
 int launch_lse_reduce(const float* parts, int P, int n, float in_mul, float out_mul, float* out, cudaStream_t st) {
   int blocks = (n + 31) / 32;
   if (blocks > num_sms() * 8) blocks = num_sms() * 8;
@@ -342,6 +395,47 @@ __global__ void __launch_bounds__(256) lse_combine_ptrs_kernel(const float* cons
   }
 }
 
+// Column-LSE combine over the W peer buffers + this rank's loss + the exchange epoch bump, in ONE launch.  Blocks
+// [0, gridDim.x - 1) combine all n columns; the LAST block recomputes the combine for the rank's own M label columns
+// (W loads each) and reduces  0.5 * mean_i(row_lse_i + col_lse[off + i] - 2 diag_i)  in fp64, so no block waits for
+// another.  epoch (optional) is the device counter of the flag-gated forward: bumped here, at the end of a forward,
+// for the next one.
+__global__ void __launch_bounds__(256) lse_combine_loss_kernel(const float* const* __restrict__ parts, int W, int n,
+                                                               float* __restrict__ out,
+                                                               const float* __restrict__ row_lse,
+                                                               const float* __restrict__ diag, int M, int label_offset,
+                                                               float* __restrict__ loss_out, int* __restrict__ epoch) {
+  auto combine = [&](int i) {
+    float v[16];
+    float mx = -INFINITY;
+    for (int w = 0; w < W; ++w) {
+      v[w] = parts[w][i] * kLog2e;
+      mx = fmaxf(mx, v[w]);
+    }
+    float l = 0.f;
+    for (int w = 0; w < W; ++w) l += exp2f(v[w] - mx);
+    return (mx + log2f(l)) * kLn2;
+  };
+  if (blockIdx.x + 1 < gridDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (gridDim.x - 1) * blockDim.x) out[i] = combine(i);
+    return;
+  }
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < M; i += blockDim.x)
+    s += (double)row_lse[i] + (double)combine(label_offset + i) - 2.0 * (double)diag[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    loss_out[0] = (float)(0.5 * t / (double)M);
+    if (epoch) epoch[0] += 1;
+  }
+}
+
 // out[i] = sum_w parts[w][i]  (bf16 in, fp32 accumulate, bf16 out): the reduce step of the pull-based reduce-scatter
 __global__ void __launch_bounds__(256) sum_ptrs_bf16_kernel(const __nv_bfloat16* const* __restrict__ parts, int W,
                                                             size_t n8, __nv_bfloat16* __restrict__ out) {
@@ -375,6 +469,36 @@ extern "C" int xtag_lse_combine_ptrs(const float* const* parts_dev, int W, int N
   int blocks = (N + 255) / 256;
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
   lse_combine_ptrs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(parts_dev, W, N, out);
+  XTAG_CHECK_LAUNCH();
+  return XTAG_OK;
+}
+
+extern "C" int xtag_lse_combine_ptrs_loss(const float* const* parts_dev, int W, int N, float* col_out,
+                                          const float* row_lse, const float* diag, int M, int label_offset,
+                                          float* loss_out, int* epoch, void* stream) {
+  XTAG_REQUIRE(parts_dev && col_out && row_lse && diag && loss_out && W > 0 && W <= 16 && N > 0 && M > 0 &&
+                   label_offset >= 0 && (long)label_offset + M <= (long)N,
+               XTAG_ERR_INVALID, "lse_combine_ptrs_loss: bad arguments");
+  int blocks = (N + 255) / 256;
+  if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+  lse_combine_loss_kernel<<<blocks + 1, 256, 0, (cudaStream_t)stream>>>(parts_dev, W, N, col_out, row_lse, diag, M,
+                                                                       label_offset, loss_out, epoch);
+  XTAG_CHECK_LAUNCH();
+  return XTAG_OK;
+}
+
+extern "C" int xtag_lse_reduce2_log2(const float* parts0, int P0, int n0, float* out0, const float* parts1, int P1,
+                                     int n1, float* out1, void* stream) {
+  XTAG_REQUIRE(parts0 && out0 && parts1 && out1 && P0 > 0 && n0 > 0 && P1 > 0 && n1 > 0, XTAG_ERR_INVALID,
+               "lse_reduce2_log2: bad arguments");
+  Reduce2 r;
+  r.parts[0] = parts0; r.parts[1] = parts1;
+  r.out[0] = out0; r.out[1] = out1;
+  r.P[0] = P0; r.P[1] = P1;
+  r.n[0] = n0; r.n[1] = n1;
+  r.nb0 = (n0 + 31) / 32;
+  const int blocks = r.nb0 + (n1 + 31) / 32;
+  lse_reduce2_kernel<<<blocks, 512, 0, (cudaStream_t)stream>>>(r);
   XTAG_CHECK_LAUNCH();
   return XTAG_OK;
 }

@@ -972,6 +972,10 @@ static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, in
 
 int launch_lse_reduce(const float* parts, int P, int n, float in_mul, float out_mul, float* out, cudaStream_t st);
 int launch_sum_into(const float* parts, int n, float* out, cudaStream_t st);
+}  // namespace xtag
+extern "C" int xtag_lse_reduce2_log2(const float* parts0, int P0, int n0, float* out0, const float* parts1, int P1,
+                                     int n1, float* out1, void* stream);
+namespace xtag {
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -994,9 +998,7 @@ int tc_clip_fwd(const void* A, const void* Bm, int M, int N, int D, const float*
   ep.diag = diag;
   int rc = launch_tc<EPI_LSE, false, false>(A, D, Bm, D, M, N, D, ep, st);
   if (rc) return rc;
-  rc = launch_lse_reduce(ep.row_part, 2 * num_n, M, 1.f, kLn2, row_lse, st);
-  if (rc) return rc;
-  return launch_lse_reduce(ep.col_part, num_m, N, 1.f, kLn2, col_lse, st);
+  return xtag_lse_reduce2_log2(ep.row_part, 2 * num_n, M, row_lse, ep.col_part, num_m, N, col_lse, st);
 }
 
 // One column block of a forward whose reductions are deferred (chunk-pipelined multi-GPU gather): the kernel only

@@ -143,10 +143,9 @@ class CudaKernels:
         row_lse = torch.empty(st["M"], dtype=torch.float32, device=dev)
         col = st["col_out"] if st["col_out"] is not None else torch.empty(st["N"], dtype=torch.float32, device=dev)
         assert col.is_contiguous() and col.numel() == st["N"]
-        check(self.lib.xtag_lse_reduce_log2(_p(st["row_part"]), st["P"], st["M"], _p(row_lse), _stream()),
-              "xtag_lse_reduce_log2")
-        check(self.lib.xtag_lse_reduce_log2(_p(st["col_part"]), st["num_m"], st["N"], _p(col), _stream()),
-              "xtag_lse_reduce_log2")
+        check(self.lib.xtag_lse_reduce2_log2(_p(st["row_part"]), st["P"], st["M"], _p(row_lse),
+                                             _p(st["col_part"]), st["num_m"], st["N"], _p(col), _stream()),
+              "xtag_lse_reduce2_log2")
         return row_lse, col, st["diag"]
 
     # ---- K1 fused with the exchange: one persistent launch gated by per-block ready flags -----------------------
@@ -179,8 +178,8 @@ class CudaKernels:
         check(self.lib.xtag_clip_fwd_stream(_p(A), _p(Bm_all), _dt(A), M, N, D, _p(scale), int(label_offset),
                                             o_arr, w_arr, nblk, int(blk_cols), _p(ready_flags), _p(epoch),
                                             _p(row_part), _p(col_part), N, _p(diag), _stream()), "xtag_clip_fwd_stream")
-        check(self.lib.xtag_lse_reduce_log2(_p(row_part), rp.value, M, _p(row_lse), _stream()), "xtag_lse_reduce_log2")
-        check(self.lib.xtag_lse_reduce_log2(_p(col_part), cp.value, N, _p(col), _stream()), "xtag_lse_reduce_log2")
+        check(self.lib.xtag_lse_reduce2_log2(_p(row_part), rp.value, M, _p(row_lse), _p(col_part), cp.value, N, _p(col),
+                                             _stream()), "xtag_lse_reduce2_log2")
         return row_lse, col, diag
 
     def lse_reduce_log2(self, parts: torch.Tensor) -> torch.Tensor:
@@ -207,6 +206,18 @@ class CudaKernels:
         out = torch.empty(N, dtype=torch.float32, device=ptrs_dev.device)
         check(self.lib.xtag_lse_combine_ptrs(_p(ptrs_dev), W, N, _p(out), _stream()), "xtag_lse_combine_ptrs")
         return out
+
+    def lse_combine_ptrs_loss(self, ptrs_dev: torch.Tensor, W: int, N: int, row_lse: torch.Tensor, diag: torch.Tensor,
+                              label_offset: int, epoch: Optional[torch.Tensor] = None):
+        """-> (col_lse [N], loss 0-d): combine of the W peer buffers, this rank's loss and (optionally) the bump of the
+        exchange epoch in one launch."""
+        _cuda(ptrs_dev, row_lse, diag, epoch)
+        out = torch.empty(N, dtype=torch.float32, device=ptrs_dev.device)
+        loss = torch.empty((), dtype=torch.float32, device=ptrs_dev.device)
+        check(self.lib.xtag_lse_combine_ptrs_loss(_p(ptrs_dev), W, N, _p(out), _p(row_lse), _p(diag), row_lse.numel(),
+                                                  int(label_offset), _p(loss), _p(epoch), _stream()),
+              "xtag_lse_combine_ptrs_loss")
+        return out, loss
 
     def sum_ptrs_bf16(self, ptrs_dev: torch.Tensor, W: int, shape) -> torch.Tensor:
         _cuda(ptrs_dev)
@@ -237,7 +248,8 @@ class CudaKernels:
         if need_dB:
             dB = dB_out if dB_out is not None else torch.empty((N, D), dtype=grad_dtype, device=dev)
             assert dB.is_contiguous() and dB.shape == (N, D) and dB.dtype == grad_dtype
-        dscale = torch.zeros((), dtype=torch.float32, device=dev)
+        # (a reuse_ds call never writes dscale: no fill kernel for it)
+        dscale = None if reuse_ds else torch.zeros((), dtype=torch.float32, device=dev)
         g = grad_out.detach().to(torch.float32).reshape(1).contiguous()
         nbytes = int(self.lib.xtag_clip_bwd_ws_bytes(M, N, D, _dt(A), self.impl))
         if nbytes == 0:

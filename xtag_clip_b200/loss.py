@@ -182,6 +182,7 @@ class _FusedClipLoss(torch.autograd.Function):
         scale = _as_scale_tensor(logit_scale, img.device)
         b = img.shape[0]
         img_all = txt_all = None
+        loss = None
         if W == 1:
             off = 0
             row_lse, col_lse, diag = K.clip_fwd(img, txt, scale, 0)
@@ -246,7 +247,10 @@ class _FusedClipLoss(torch.autograd.Function):
                 row_lse = K.lse_combine(torch.stack(row_parts)) if len(row_parts) > 1 else row_parts[0]
             if sx is not None:
                 sx.end_gather(streamed)
-                col_lse = sx.combine_cols(K)                      # barrier + one kernel over the W peer buffers
+                if hasattr(sx, "combine_cols_loss"):              # barrier + one kernel: combine, loss, epoch bump
+                    col_lse, loss = sx.combine_cols_loss(K, row_lse, diag, off, streamed)
+                else:
+                    col_lse = sx.combine_cols(K)                  # barrier + one kernel over the W peer buffers
                 ctx.symm = (sx, sx.step)
             else:
                 side = cfg.comm.side_stream(txt.device)
@@ -267,7 +271,8 @@ class _FusedClipLoss(torch.autograd.Function):
             img_all = cfg.comm.all_gather_cat(img)
             txt_all = cfg.comm.all_gather_cat(txt)
             row_lse, col_lse, diag = K.clip_fwd(img_all, txt_all, scale, 0)
-        loss = K.clip_loss(row_lse, diag, col_lse, off)
+        if loss is None:
+            loss = K.clip_loss(row_lse, diag, col_lse, off)
         if not hasattr(ctx, "symm"):
             ctx.symm = None
         if not hasattr(ctx, "pushed"):

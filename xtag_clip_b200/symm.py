@@ -73,7 +73,8 @@ class SymmExchange:
         # streamed forward: per-block ready flags, written by the copy stream right behind each pulled block with the
         # step's epoch value (a device counter, so a captured step replays with fresh values)
         self.flags = torch.zeros(world, dtype=torch.int32, device=device)
-        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        # the epoch of the NEXT flag-gated forward; bumped on the device at the end of each one (combine_cols_loss)
+        self.epoch = torch.ones(1, dtype=torch.int32, device=device)
         self._streamed_two = False        # the last streamed gather forked the second copy stream
         self._pushed = False              # the push exchange is in use (its backward ends with a slot-release barrier)
         self.gbuf = None                  # push exchange: peer-writable gather buffers, allocated on first use
@@ -137,7 +138,6 @@ class SymmExchange:
         order: it waits per block)."""
         b, s, W, r = self.b, self.slot, self.W, self.r
         cur = torch.cuda.current_stream()
-        self.epoch.add_(1)                                  # compute stream, before the fork: ordered before K1 reads it
         out_all[r * b:(r + 1) * b].copy_(x)
         self.s1.wait_stream(cur)
         order = [(r + j) % W for j in range(W)]
@@ -188,7 +188,6 @@ class SymmExchange:
         gbuf, pflags = self._push_buffers()
         b, s, W, r = self.b, self.slot, self.W, self.r
         cur = torch.cuda.current_stream()
-        self.epoch.add_(1)
         gbuf[s][r * b:(r + 1) * b].copy_(x)
         self.s1.wait_stream(cur)
         if not torch.cuda.is_current_stream_capturing():    # (a captured backward joins s3 itself before it ends)
@@ -238,6 +237,18 @@ class SymmExchange:
     def combine_cols(self, K) -> torch.Tensor:
         self.h_col.barrier(channel=1)                       # on the compute stream: all K1 launches precede it
         return K.lse_combine_ptrs(self.col_ptrs[self.slot], self.W, self.B)
+
+    def combine_cols_loss(self, K, row_lse: torch.Tensor, diag: torch.Tensor, label_offset: int, streamed: bool):
+        """barrier + ONE kernel: combined column LSEs [B], this rank's loss, and (flag-gated forward) the bump of the
+        exchange epoch for the next step.  -> (col_lse, loss)"""
+        self.h_col.barrier(channel=1)
+        if hasattr(K, "lse_combine_ptrs_loss"):
+            return K.lse_combine_ptrs_loss(self.col_ptrs[self.slot], self.W, self.B, row_lse, diag, label_offset,
+                                           self.epoch if streamed else None)
+        col = K.lse_combine_ptrs(self.col_ptrs[self.slot], self.W, self.B)
+        if streamed:
+            self.epoch.add_(1)
+        return col, K.clip_loss(row_lse, diag, col, label_offset)
 
     # ---- backward: reduce-scatter of the text-gradient partials -----------------------------------------------
     def dT_buffer(self) -> torch.Tensor:
