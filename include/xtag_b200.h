@@ -69,6 +69,7 @@ uint64_t    xtag_launch_count(void);
  *   bit 24       do NOT use the CTA-pair kernels (tcgen05.mma.cta_group::2, 256 x 256 tiles per pair of SMs, 6-stage
  *                operand ring); default: pair kernels whenever the problem has more than 128 rows
  *   bits 25, 26  L2 evict_last on the B / A operand tile loads
+ *   bit 27       plain GEMMs: never split the K loop
  * Initial value: environment variable XTAG_TC_TUNE (0x200800 if unset).  set returns the previous value. */
 int         xtag_set_tune(int bits);
 int         xtag_get_tune(void);
@@ -187,6 +188,14 @@ int xtag_clip_bwd(const void* A, const void* Bm, int dtype, int M, int N, int D,
                                      skip the dS producer and d(logit_scale) (lets a caller launch the dB GEMM, start
                                      its reduce-scatter, and overlap it with the dA GEMM) */
 
+/* Dense layer on the tcgen05 kernels (the tag head's K|V projections):
+ *   C[M, N] (bf16, row stride ldc) = A[M, K] (bf16, row stride lda) * W[N, K]^T + bias[N] (fp32, may be NULL)
+ * W is an nn.Linear weight as it lies in memory; Linear layers reading the same input are fused by concatenating their
+ * weights along N (reference tagging_heads/bert.py:208-209: key and value of both layers = one [D -> 4*768] GEMM).
+ * C leaves through TMA tile stores.  K, lda, ldc multiples of 8. */
+int xtag_tc_linear_bf16(const void* A, long lda, const void* W, const float* bias, void* C, long ldc,
+                        int M, int N, int K, void* stream);
+
 /* plain tcgen05 GEMM used by K2 and exported for bring-up tests:
  *   C[M,N] = alpha * A[M,K] * B[N,K]^T   (A, B bf16 row-major "K-major"; C f32 or bf16; alpha by value) */
 int xtag_tc_gemm_nt(const void* A, const void* B, void* C, int c_dtype,
@@ -196,6 +205,12 @@ int xtag_tc_gemm_nt(const void* A, const void* B, void* C, int c_dtype,
  * {(0,0), (0,1), (1,1)}: the three layouts K2 uses (S = A Bm^T, dA = dS Bm, dB = dS^T A). */
 int xtag_tc_gemm(const void* A, const void* B, void* C, int c_dtype,
                  int M, int N, int K, float alpha, int a_mn, int b_mn, void* stream);
+/* Same with a workspace of xtag_tc_gemm_ws_bytes(M, N, K) bytes (0 = none needed): outputs with few 128/256 x 256
+ * tiles and a long K are computed split-K -- S slices of the K loop run as S x tiles work items into fp32 partial slabs
+ * in `ws`, one small kernel sums them in a fixed order.  Without a workspace the K loop is never split. */
+size_t xtag_tc_gemm_ws_bytes(int M, int N, int K);
+int xtag_tc_gemm_ex(const void* A, const void* B, void* C, int c_dtype, int M, int N, int K, float alpha,
+                    int a_mn, int b_mn, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  tag-head cross-attention core.  Replaces the eager attention in
@@ -221,6 +236,13 @@ int xtag_xattn_bwd(const void* q, const void* k, const void* v, const void* o, c
                    int ldq, int ldk, int ldv,
                    float softmax_scale, float dropout_p, uint64_t seed, uint64_t offset,
                    void* ws, size_t ws_bytes, void* stream);
+/* Same with dK / dV written as column slices of wider buffers (row strides lddk / lddv in elements), so that the
+ * gradients of several attention layers that share one fused K|V projection buffer land in ONE [b*Lk, ...] gradient
+ * buffer and feed one projection-backward GEMM.  bf16 single-pass kernel only (XTAG_ERR_UNSUPPORTED otherwise). */
+int xtag_xattn_bwd_ld(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                      int dtype, void* dq, void* dk, void* dv, int b, int Lq, int Lk, int heads, int dh, int ldq,
+                      int ldk, int ldv, int lddk, int lddv, float softmax_scale, float dropout_p, uint64_t seed,
+                      uint64_t offset, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K5  AsymmetricLoss forward + d/dx in one pass.  Replaces AsymmetricLoss.forward

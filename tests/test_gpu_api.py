@@ -167,6 +167,39 @@ def test_tag_head_bf16_config3_shape():
     assert rel_err(logits.float(), ref) < 3e-2
 
 
+def test_tag_head_bf16_config3_full_batch_fwd_bwd():
+    """BASELINE config 3 at its real size (tokens [1024, 197, 512], bf16 autocast, eval): forward AND token / weight
+    gradients of the production path (fused K|V projection GEMM + K4) against the fp64 oracle on a 32-sample slice
+    (samples are independent; bars: logits 3e-2, gradients 5e-2 max-norm), and against the unfused path (one library
+    Linear per projection) on the full batch."""
+    D, b, N, ns = 512, 1024, 197, 32
+    params = make_tag_params(11, D, gain=4.0, dtype=torch.float32)
+    heads = [xt.TagHead(D, fuse_kv=f).cuda() for f in (True, False)]
+    for h in heads:
+        h.load_state_dict(params, strict=True)
+        h.eval()
+    g = torch.Generator().manual_seed(12)
+    tokens = torch.randn(b, N, D, generator=g)
+    wgt = torch.randn(b, 44, generator=g)
+    outs = []
+    for h in heads:
+        tok = tokens.cuda().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = h.tag_forward(tok)
+        (logits.float() * wgt.cuda()).sum().backward()
+        kw = h.tag_head.encoder.layer[1].crossattention.self.key.weight.grad
+        vb = h.tag_head.encoder.layer[0].crossattention.self.value.bias.grad
+        outs.append((logits.float().detach(), tok.grad.detach(), kw.detach().clone(), vb.detach().clone()))
+    for a, c, tol in zip(outs[0], outs[1], (4e-2, 4e-2, 4e-2, 4e-2)):    # two bf16 pipelines, max-norm
+        assert rel_err(a, c) < tol, rel_err(a, c)
+    p64 = {k: v.double() for k, v in params.items()}
+    tok64 = tokens[:ns].double().requires_grad_(True)
+    ref = oracle.tag_head_forward(tok64, p64)
+    (ref * wgt[:ns].double()).sum().backward()
+    assert rel_err(outs[0][0][:ns], ref) < 3e-2
+    assert rel_err(outs[0][1][:ns], tok64.grad) < 5e-2
+
+
 def test_asymmetric_loss_and_l2_api(golden_dir):
     g = np.load(os.path.join(golden_dir, "asl.npz"))
     x = torch.from_numpy(g["x"]).float().cuda().requires_grad_(True)

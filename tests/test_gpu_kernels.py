@@ -479,3 +479,61 @@ def test_lse_reduce2_and_combine_loss(K):
     lref = 0.5 * (row.double() + cref[off:off + M] - 2 * diag.double()).mean()
     assert rel_err(col, cref) < 1e-6 and abs(float(loss) - float(lref)) < 1e-5 * abs(float(lref)) and int(epoch) == 42
     assert rel_err(K.lse_combine_ptrs(ptrs, W, N), cref) < 1e-6
+
+
+@pytest.mark.parametrize("M,N,Kd", [(256, 512, 128), (1000, 3072, 512), (197 * 33, 3072, 768), (130, 264, 72), (64, 8, 8)])
+def test_tc_linear_bias_epilogue(K, M, N, Kd):
+    """Dense layer on the tcgen05 kernels (bias epilogue, bf16 TMA tile stores): the fused K|V projection of the tag
+    head (bert.py:208-209), against torch on the same bf16 operands; ragged M / N edges are clipped by the TMA unit."""
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, Kd, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, Kd, generator=g) * 0.05).bfloat16().cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    y = K.tc_linear(x, w, bias)
+    ref = x.float() @ w.float().T + bias
+    assert y.dtype == torch.bfloat16 and rel_err(y.float(), ref) < 6e-3          # one bf16 rounding of the output
+    assert rel_err(K.tc_linear(x, w, None).float(), x.float() @ w.float().T) < 6e-3
+
+
+@pytest.mark.parametrize("b,Lq,Lk,p", [(5, 44, 197, 0.0), (3, 44, 50, 0.1), (2, 16, 257, 0.0)])
+def test_xattn_bwd_strided_dkv(K, b, Lq, Lk, p):
+    """dK / dV written as column slices of one wider gradient buffer (xtag_xattn_bwd_ld) == the contiguous outputs."""
+    g = torch.Generator().manual_seed(Lk)
+    H, heads = 768, 4
+    q = torch.randn(b, Lq, H, generator=g).bfloat16().cuda()
+    kv = torch.randn(b, Lk, 4 * H, generator=g).bfloat16().cuda()
+    k, v = kv[..., H:2 * H], kv[..., 3 * H:]
+    sc = 1 / math.sqrt(H // heads)
+    o, lse = K.xattn_fwd(q, k, v, heads, sc, p, 7, 3)
+    do = torch.randn(b, Lq, H, generator=g).bfloat16().cuda()
+    dq0, dk0, dv0 = K.xattn_bwd(q, k, v, o, do, lse, heads, sc, p, 7, 3)
+    buf = torch.full((b, Lk, 4 * H), 7.0, dtype=torch.bfloat16, device="cuda")
+    dq1, dk1, dv1 = K.xattn_bwd(q, k, v, o, do, lse, heads, sc, p, 7, 3, dk_out=buf[..., :H], dv_out=buf[..., 2 * H:3 * H])
+    assert torch.equal(dq0, dq1) and torch.equal(dk0, buf[..., :H]) and torch.equal(dv0, buf[..., 2 * H:3 * H])
+    assert dk1.data_ptr() == buf.data_ptr() and bool((buf[..., H:2 * H] == 7.0).all()) and bool((buf[..., 3 * H:] == 7.0).all())
+
+
+@pytest.mark.parametrize("M,N,Kd,a_mn,b_mn", [(3072, 512, 197 * 64, True, True), (256, 256, 4096, False, False),
+                                               (512, 1024, 8192, False, True), (384, 200, 2048 + 72, True, True),
+                                               (4096, 512, 4096, False, True)])
+def test_tc_gemm_split_k(K, M, N, Kd, a_mn, b_mn):
+    """Plain GEMMs whose output has few tiles and a long K run split-K (S slices of the K loop as S x tiles work items,
+    fp32 partial slabs in the caller's workspace, summed in a fixed order): the tag head's projection weight gradient
+    shape and the gradient GEMMs of small-batch contrastive steps, fp32 and bf16 outputs, against torch -- and
+    bit-identical between two runs (deterministic reduction)."""
+    assert K.lib.xtag_tc_gemm_ws_bytes(M, N, Kd) > 0
+    g = torch.Generator().manual_seed(M + Kd)
+    A = (torch.randn(M, Kd, generator=g) * 0.1).bfloat16().cuda()
+    B = (torch.randn(N, Kd, generator=g) * 0.1).bfloat16().cuda()
+    ref = A.float() @ B.float().T
+    Aop = A.T.contiguous() if a_mn else A
+    Bop = B.T.contiguous() if b_mn else B
+    c32 = K.tc_gemm(Aop, Bop, a_mn, b_mn, torch.float32)
+    assert rel_err(c32, ref) < 2e-5
+    assert torch.equal(c32, K.tc_gemm(Aop, Bop, a_mn, b_mn, torch.float32))
+    assert rel_err(K.tc_gemm(Aop, Bop, a_mn, b_mn, torch.bfloat16, alpha=0.5).float(), 0.5 * ref) < 6e-3
+    old = K.lib.xtag_set_tune(K.lib.xtag_get_tune() | 0x8000000)          # bit 27: never split
+    try:
+        assert rel_err(K.tc_gemm(Aop, Bop, a_mn, b_mn, torch.float32), ref) < 2e-5
+    finally:
+        K.lib.xtag_set_tune(old)

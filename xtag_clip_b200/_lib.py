@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libxtag_b200.so")
 XTAG_F32, XTAG_BF16 = 0, 1
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 BWD_REUSE_DS = 1
+ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = -1, -2, -3, -4
 
 _lib = None
 
@@ -50,7 +51,16 @@ SIGNATURES = {
     "xtag_clip_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                               c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
                               c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "xtag_tc_linear_bf16": (c_int, [c_void_p, ctypes.c_long, c_void_p, c_void_p, c_void_p, ctypes.c_long, c_int, c_int, c_int,
+                                    c_void_p]),
+    "xtag_xattn_bwd_ld": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                  c_void_p, c_void_p, c_void_p,
+                                  c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_float, c_float, c_uint64, c_uint64, c_void_p, c_size_t, c_void_p]),
     "xtag_tc_gemm_nt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "xtag_tc_gemm_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "xtag_tc_gemm_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,
+                                c_size_t, c_void_p]),
     "xtag_tc_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
     "xtag_xattn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -52,7 +52,7 @@ struct Geo {
 };
 constexpr int kMaxStages = 6;
 
-enum { EPI_LSE = 0, EPI_DS = 1, EPI_STORE = 2 };
+enum { EPI_LSE = 0, EPI_DS = 1, EPI_STORE = 2, EPI_BIAS = 3 };
 
 struct EpiParams {
   // EPI_LSE
@@ -76,6 +76,12 @@ struct EpiParams {
   int c_is_bf16;
   float alpha;            // C = alpha * (alpha_p ? *alpha_p : 1) * acc
   const float* alpha_p;
+  // EPI_BIAS: C (bf16, row stride ldc, written by TMA tile stores) = alpha * acc + bias[column]
+  const float* bias;      // [N] fp32 or nullptr
+  // EPI_STORE split-K: the K loop is cut into split_k slices, scheduled as split_k x tiles work items; slice ks writes
+  // its raw fp32 partial to C + ks * split_stride (a workspace), a second kernel sums the slices into the real output
+  int split_k;            // 0 / 1: no split
+  long split_stride;      // elements between consecutive partial slabs
   // streamed forward (EPI_LSE over a gather buffer that fills up block by block): column block k of blk_tiles n tiles
   // is is one slab of the tile schedule, slabs are visited in arrival order; ready_flags[blk] == *epoch_p once block blk has landed
   const int* ready_flags; // device [nblk] or nullptr
@@ -92,6 +98,7 @@ constexpr int kTunePrefetchMask = 0xff, kTuneStoreEvictFirst = 0x100, kTuneStrea
               kTuneCluster4 = 0x8000,       // clusters of 4
               kTuneDbgNoDsStore = 0x1000,   // diagnostics only (wrong results): dS tile neither staged nor stored
               kTuneDbgNoDsTma = 0x2000,     // diagnostics only (wrong results): dS tile staged in smem, TMA store skipped
+              kTuneNoSplitK = 0x8000000,    // plain GEMMs: never split the K loop
               kTuneNoPair = 0x1000000,      // do NOT use the CTA-pair (cta_group::2) kernels
               kTuneBEvictLast = 0x2000000,  // B operand tiles: L2 evict_last
               kTuneAEvictLast = 0x4000000;  // A operand tiles: L2 evict_last
@@ -378,7 +385,8 @@ __device__ __forceinline__ float ds_tile(const EpiParams& ep, const CUtensorMap*
 }
 
 // plain GEMM epilogue: C = alpha * acc (fp32 or bf16)
-__device__ __forceinline__ void store_tile(const EpiParams& ep, uint32_t taddr, int gi, int n_base, int M, int N) {
+__device__ __forceinline__ void store_tile(const EpiParams& ep, uint32_t taddr, int gi, int n_base, int M, int N,
+                                           long c_off) {
   const float alpha = ep.alpha * (ep.alpha_p ? ep.alpha_p[0] : 1.f);
   const bool row_ok = gi < M;
 #pragma unroll 1
@@ -407,7 +415,7 @@ __device__ __forceinline__ void store_tile(const EpiParams& ep, uint32_t taddr, 
           if (c0 + j < N) dst[j] = __float2bfloat16_rn(__uint_as_float(r[j]) * alpha);
       }
     } else {
-      float* dst = reinterpret_cast<float*>(ep.C) + (size_t)gi * ep.ldc + c0;
+      float* dst = reinterpret_cast<float*>(ep.C) + c_off + (size_t)gi * ep.ldc + c0;
       if (c0 + 32 <= N && (ep.ldc % 4) == 0) {
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4)
@@ -419,6 +427,44 @@ __device__ __forceinline__ void store_tile(const EpiParams& ep, uint32_t taddr, 
         for (int j = 0; j < 32; ++j)
           if (c0 + j < N) dst[j] = __uint_as_float(r[j]) * alpha;
       }
+    }
+  }
+}
+
+// dense-layer epilogue: C = bf16(alpha * acc + bias[col]) through the same per-warp staging + TMA tile stores as the dS
+// producer (a [b*N, 3072] K|V projection writes > 1 GB: direct 16-byte stores per thread-row would issue 32 L2 requests
+// per warp instruction); rows / columns past the edge are clipped by the TMA unit
+__device__ __forceinline__ void bias_tile(const EpiParams& ep, const CUtensorMap* tmC, uint32_t taddr, uint32_t ostage,
+                                          int row_blk, int n_base, int lane, int N) {
+  const float alpha = ep.alpha;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + ch * 32, r);
+    tmem_ld_wait();
+    const int c0 = n_base + ch * 32;
+    if (c0 >= N) continue;                                  // warp-uniform
+    float d[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float bj = (ep.bias && c0 + j < N) ? __ldg(ep.bias + c0 + j) : 0.f;
+      d[j] = fmaf(__uint_as_float(r[j]), alpha, bj);
+    }
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint32_t p0 = pack2_bf16(d[u * 8 + 0], d[u * 8 + 1]), p1 = pack2_bf16(d[u * 8 + 2], d[u * 8 + 3]);
+      uint32_t p2 = pack2_bf16(d[u * 8 + 4], d[u * 8 + 5]), p3 = pack2_bf16(d[u * 8 + 6], d[u * 8 + 7]);
+      const uint32_t off = (uint32_t)(lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ostage + off), "r"(p0), "r"(p1), "r"(p2), "r"(p3)
+                   : "memory");
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmC, ostage, c0, row_blk);
+      tma_store_commit();
     }
   }
 }
@@ -463,8 +509,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   // scheduled tiles: BM*CG rows x BN columns (a CTA pair works on two vertically adjacent 128-row blocks)
   const int num_m = (M + BM * CG - 1) / (BM * CG), num_n = (N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
-  const int num_k = (K + BK - 1) / BK;
+  const int num_k_all = (K + BK - 1) / BK;
+  // split-K (plain GEMM only): work item = tile * S + slice; the S slices of a tile run side by side
+  const int S = (EPI == EPI_STORE && ep.split_k > 1) ? ep.split_k : 1;
+  const int kb_per = (num_k_all + S - 1) / S;
+  const int num_tiles = num_m * num_n * S;
   constexpr int kGroup = kGroupM / CG;            // same operand footprint per wave in both modes
   const int tile_first = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -507,7 +556,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const int pf_dist = (CG == 1) ? (ep.tune & kTunePrefetchMask) : 0;
+      const int pf_dist = (CG == 1 && S == 1) ? (ep.tune & kTunePrefetchMask) : 0;
       // bit 9: the A operand of the plain GEMMs is the staged dS, read exactly once: mark it evict_first so that the
       // stream does not push the re-used B operand (the feature matrix) out of L2
       const uint64_t a_policy = (EPI == EPI_STORE && (ep.tune & kTuneStreamAEvictFirst)) ? l2_policy_evict_first()
@@ -583,7 +632,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int epoch = (streamed && ep.ready_flags) ? ep.epoch_p[0] : 0;
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         int m_blk, n_blk, s_idx;
-        tile_coords(tile, num_m, num_n, slab, slab_order, m_blk, n_blk, &s_idx, kGroup);
+        const int t_idx = tile / S, ks = tile - t_idx * S;
+        const int kb_begin = ks * kb_per, num_k = min(num_k_all, kb_begin + kb_per);
+        tile_coords(t_idx, num_m, num_n, slab, slab_order, m_blk, n_blk, &s_idx, kGroup);
         if constexpr (CG == 2) m_blk = m_blk * 2 + (int)cta_rank;
         if (streamed && s_idx != slab_seen) {
           // first tile of this CTA in a new column block: its rows of the gather buffer must have landed (the copy
@@ -597,7 +648,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int m_nxt = -1, n_nxt = -1;
         if (pf_dist && tile + tile_step < num_tiles)
           tile_coords(tile + tile_step, num_m, num_n, slab, slab_order, m_nxt, n_nxt, nullptr, kGroup);
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb_begin; kb < num_k; ++kb) {
           if (pf_dist == 0xff) {
             // de-duplicated next-tile prefetch: the CTAs of a wave share operand tiles (16 CTAs per B tile, ~9 per A
             // tile), so only ONE of them asks L2 for each tile of the wave's next position, a whole tile ahead:
@@ -663,6 +714,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const int ks = tile % S;
+        const int num_k = min(num_k_all, ks * kb_per + kb_per) - ks * kb_per;     // k-blocks of this slice (>= 1)
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
@@ -701,7 +754,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     [[maybe_unused]] const uint64_t store_policy = (ep.tune & kTuneStoreEvictFirst) ? l2_policy_evict_first() : 0;
     for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
       int m_blk, n_blk;
-      tile_coords(tile, num_m, num_n, slab, slab_order, m_blk, n_blk, nullptr, kGroup);
+      const int t_idx = tile / S;
+      [[maybe_unused]] const int ks = tile - t_idx * S;
+      tile_coords(t_idx, num_m, num_n, slab, slab_order, m_blk, n_blk, nullptr, kGroup);
       if constexpr (CG == 2) m_blk = m_blk * 2 + (int)cta_rank;
       const int gi = m_blk * BM + q * 32 + lane;          // this thread's row
       const int n_base = n_blk * BN + h * 128;            // first column of this warp's half
@@ -790,16 +845,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_tempty<CG>(tempty);
+      } else if constexpr (EPI == EPI_BIAS) {
+        mbar_wait(tfull, acc_phase);
+        tc_fence_after();
+        bias_tile(ep, &tmC, taddr, smem_u32(out_stage + e * 2048), m_blk * BM + q * 32, n_base, lane, N);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_tempty<CG>(tempty);
       } else {
         mbar_wait(tfull, acc_phase);
         tc_fence_after();
-        store_tile(ep, taddr, gi, n_base, M, N);
+        store_tile(ep, taddr, gi, n_base, M, N, (S > 1) ? (long)ks * ep.split_stride : 0L);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_tempty<CG>(tempty);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if constexpr (EPI == EPI_BIAS) {
+      if (lane == 0) tma_store_wait_all();
     }
     if constexpr (EPI == EPI_DS) {
       if (lane == 0) tma_store_wait_all();               // dS tiles fully written before the kernel ends
@@ -889,6 +954,10 @@ static int launch_tc_cl(const void* A, long lda, const void* B, long ldb, int M,
     int rcC = make_store_tmap_bf16(&tmC, ep.dS, M, N, ep.ldds);
     if (rcC) return rcC;
   }
+  if (EPI == EPI_BIAS) {
+    int rcC = make_store_tmap_bf16(&tmC, ep.C, M, N, ep.ldc);
+    if (rcC) return rcC;
+  }
   int rc = A_MN ? make_tmap_bf16(&tmA, A, K, M, lda, BK) : make_tmap_bf16(&tmA, A, M, K, lda, BM);
   if (rc) return rc;
   // K-major B: each CTA of a cluster fetches BN / CL rows of the shared tile
@@ -953,7 +1022,7 @@ static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, in
                      cudaStream_t st, int* grid_used = nullptr) {
   EpiParams ep = ep_in;
   ep.tune = tc_tune();
-  const int num_n = (N + BN - 1) / BN;
+  const int num_n = (N + BN - 1) / BN * ((EPI == EPI_STORE && ep.split_k > 1) ? ep.split_k : 1);   // x K slices
   if (pick_pair(M, ep.tune)) {
     const int num_pairs = ((M + 2 * BM - 1) / (2 * BM)) * num_n;
     int grid = num_sms() & ~1;
@@ -972,12 +1041,71 @@ static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, in
 
 int launch_lse_reduce(const float* parts, int P, int n, float in_mul, float out_mul, float* out, cudaStream_t st);
 int launch_sum_into(const float* parts, int n, float* out, cudaStream_t st);
+
+// ---- split-K for the plain GEMMs -----------------------------------------------------------------------------------
+// A GEMM with few output tiles and a long K (the tag head's projection weight gradient: [3072, 512] over K = b*N =
+// 201 728; the gradient GEMMs of small-batch contrastive steps) leaves most SMs idle with one work item per tile:
+// its K loop is cut into S slices that run as S x tiles work items and write raw fp32 partial slabs; one small kernel
+// sums the slabs (fixed order: deterministic) and casts.
+static int pick_split(int M, int N, int K, int tune) {
+  if (tune & kTuneNoSplitK) return 1;
+  const bool pair = pick_pair(M, tune);
+  // (the multicast clusters of the single-CTA kernels take CONSECUTIVE m tiles of one n tile: not with K slices)
+  if (!pair && (tune & (kTuneCluster2 | kTuneCluster4))) return 1;
+  const int units = pair ? num_sms() / 2 : num_sms();
+  const int tiles = ((M + (pair ? 2 : 1) * BM - 1) / ((pair ? 2 : 1) * BM)) * ((N + BN - 1) / BN);
+  const int num_k = (K + BK - 1) / BK;
+  if (tiles * 2 > units || num_k < 16) return 1;
+  int S = units / tiles;
+  if (S > num_k / 8) S = num_k / 8;
+  if (S > 32) S = 32;
+  if (S < 2) return 1;
+  const int per = (num_k + S - 1) / S;
+  return (num_k + per - 1) / per;                    // every slice owns at least one k-block
+}
+static size_t split_ws_bytes(int M, int N, int K, int tune) {
+  const int S = pick_split(M, N, K, tune);
+  return S > 1 ? (size_t)S * (size_t)M * (size_t)N * 4 : 0;
+}
+
+__global__ void __launch_bounds__(256) split_reduce_kernel(const float* __restrict__ slabs, int S, size_t stride, int M,
+                                                           int N, void* __restrict__ out, long ldc, int out_bf16) {
+  const size_t n = (size_t)M * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < S; ++k) acc += slabs[(size_t)k * stride + i];
+    const size_t r = i / N, c = i - r * N;
+    if (out_bf16) reinterpret_cast<__nv_bfloat16*>(out)[r * ldc + c] = __float2bfloat16_rn(acc);
+    else          reinterpret_cast<float*>(out)[r * ldc + c] = acc;
+  }
+}
 }  // namespace xtag
 extern "C" int xtag_lse_reduce2_log2(const float* parts0, int P0, int n0, float* out0, const float* parts1, int P1,
                                      int n1, float* out1, void* stream);
 namespace xtag {
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// plain GEMM C = alpha * A * B^T with optional split-K through the caller's workspace
+template <bool A_MN, bool B_MN>
+static int gemm_store(const void* A, long lda, const void* B, long ldb, int M, int N, int K, const EpiParams& es,
+                      void* split_ws, size_t split_bytes, cudaStream_t st) {
+  const int S = pick_split(M, N, K, tc_tune());
+  if (S > 1 && split_ws && split_bytes >= (size_t)S * M * N * 4) {
+    EpiParams ep = es;
+    ep.C = split_ws; ep.ldc = N; ep.c_is_bf16 = 0;
+    ep.split_k = S; ep.split_stride = (long)M * N;
+    int rc = launch_tc<EPI_STORE, A_MN, B_MN>(A, lda, B, ldb, M, N, K, ep, st);
+    if (rc) return rc;
+    size_t blocks = ((size_t)M * N + 255) / 256;
+    if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
+    split_reduce_kernel<<<(int)blocks, 256, 0, st>>>((const float*)split_ws, S, (size_t)M * N, M, N, es.C, es.ldc,
+                                                     es.c_is_bf16);
+    XTAG_CHECK_LAUNCH();
+    return XTAG_OK;
+  }
+  return launch_tc<EPI_STORE, A_MN, B_MN>(A, lda, B, ldb, M, N, K, es, st);
+}
 
 size_t tc_fwd_ws(int M, int N) {
   const size_t num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
@@ -1053,15 +1181,19 @@ int tc_clip_fwd_stream(const void* A, const void* Bm, int M, int N, int D, const
 // Backward workspace: dS [M][Np] bf16 (Np = N padded to 8 so rows stay 16-byte multiples) + d(logit_scale) partials.
 // The two gradient GEMMs read dS and the features in place through MN-major UMMA descriptors.
 struct BwdLayout {
-  size_t Np, off_ds, off_part, total;
+  size_t Np, off_ds, off_part, off_split, split_bytes, total;
 };
 static BwdLayout bwd_layout(int M, int N, int D) {
-  (void)D;
   BwdLayout L;
   L.Np = ((size_t)N + 7) & ~(size_t)7;
   size_t o = 0;
   L.off_ds = o;   o += align256((size_t)M * L.Np * 2);
   L.off_part = o; o += align256((size_t)256 * kEpiWarps * 4);
+  // split-K slabs of the gradient GEMMs (small problems only: large ones have enough tiles).  Sized for the
+  // default tuning so that the workspace size does not depend on a runtime knob.
+  const size_t sa = split_ws_bytes(M, D, (int)L.Np, 0), sb = split_ws_bytes(N, D, M, 0);
+  L.split_bytes = sa > sb ? sa : sb;
+  L.off_split = o; o += align256(L.split_bytes);
   L.total = o + 256;
   return L;
 }
@@ -1103,14 +1235,14 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
     // dA[i,d] = s * sum_j dS[i,j] Bm[j,d]: A operand dS is K-major (j contiguous); B operand (n=d, k=j) is the
     // feature matrix itself, [K=j rows][N=d contiguous] = MN-major
     es.C = dA;
-    rc = launch_tc<EPI_STORE, false, true>(dS, (long)L.Np, Bm, (long)D, M, D, N, es, st);
+    rc = gemm_store<false, true>(dS, (long)L.Np, Bm, (long)D, M, D, N, es, w + L.off_split, L.split_bytes, st);
     if (rc) return rc;
   }
   if (dB) {
     // dB[j,d] = s * sum_i dS[i,j] A[i,d]: A operand (m=j, k=i) is dS read as [K=i rows][M=j contiguous];
     // B operand (n=d, k=i) is A read as [K=i rows][N=d contiguous]: both MN-major, nothing is transposed
     es.C = dB;
-    rc = launch_tc<EPI_STORE, true, true>(dS, (long)L.Np, A, (long)D, N, D, M, es, st);
+    rc = gemm_store<true, true>(dS, (long)L.Np, A, (long)D, N, D, M, es, w + L.off_split, L.split_bytes, st);
     if (rc) return rc;
   }
   return XTAG_OK;
@@ -1122,8 +1254,18 @@ using namespace xtag;
 
 // C[M,N] = alpha * sum_k A(m,k) B(n,k).  a_mn == 0: A is [M][K] row-major, a_mn == 1: A is [K][M] row-major;
 // same for B with N.  Contiguous operands (leading dimension = inner extent).
+extern "C" size_t xtag_tc_gemm_ws_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return split_ws_bytes(M, N, K, 0);
+}
+
 extern "C" int xtag_tc_gemm(const void* A, const void* B, void* C, int c_dtype, int M, int N, int K, float alpha,
                             int a_mn, int b_mn, void* stream) {
+  return xtag_tc_gemm_ex(A, B, C, c_dtype, M, N, K, alpha, a_mn, b_mn, nullptr, 0, stream);
+}
+
+extern "C" int xtag_tc_gemm_ex(const void* A, const void* B, void* C, int c_dtype, int M, int N, int K, float alpha,
+                               int a_mn, int b_mn, void* ws, size_t ws_bytes, void* stream) {
   XTAG_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, XTAG_ERR_INVALID, "tc_gemm: bad arguments");
   XTAG_REQUIRE((a_mn ? M : K) % 8 == 0 && (b_mn ? N : K) % 8 == 0, XTAG_ERR_UNSUPPORTED,
                "tc_gemm: the contiguous extent of each operand must be a multiple of 8 (16-byte TMA rows)");
@@ -1134,11 +1276,28 @@ extern "C" int xtag_tc_gemm(const void* A, const void* B, void* C, int c_dtype, 
   es.C = C; es.ldc = N; es.c_is_bf16 = (c_dtype == XTAG_BF16); es.alpha = alpha; es.alpha_p = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   const long lda = a_mn ? M : K, ldb = b_mn ? N : K;
-  if (!a_mn && !b_mn) return launch_tc<EPI_STORE, false, false>(A, lda, B, ldb, M, N, K, es, st);
-  if (!a_mn && b_mn) return launch_tc<EPI_STORE, false, true>(A, lda, B, ldb, M, N, K, es, st);
-  if (a_mn && b_mn) return launch_tc<EPI_STORE, true, true>(A, lda, B, ldb, M, N, K, es, st);
+  if (!a_mn && !b_mn) return gemm_store<false, false>(A, lda, B, ldb, M, N, K, es, ws, ws_bytes, st);
+  if (!a_mn && b_mn) return gemm_store<false, true>(A, lda, B, ldb, M, N, K, es, ws, ws_bytes, st);
+  if (a_mn && b_mn) return gemm_store<true, true>(A, lda, B, ldb, M, N, K, es, ws, ws_bytes, st);
   set_error("tc_gemm: A MN-major with B K-major is not instantiated");
   return XTAG_ERR_UNSUPPORTED;
+}
+
+// Dense layer on the tcgen05 kernels: C[M, N] (bf16, row stride ldc) = A[M, K] (bf16, row stride lda) * W[N, K]^T + bias.
+// W is a torch nn.Linear weight as it lies in memory ([out, in] = K-major B operand); several Linear layers that read
+// the same input are fused by concatenating their weights along `out` (the tag head's K|V projections of both layers:
+// reference tagging_heads/bert.py:208-209).
+extern "C" int xtag_tc_linear_bf16(const void* A, long lda, const void* W, const float* bias, void* C, long ldc, int M,
+                                   int N, int K, void* stream) {
+  XTAG_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, XTAG_ERR_INVALID, "tc_linear: bad arguments");
+  XTAG_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldc % 8 == 0 && lda >= K && ldc >= N, XTAG_ERR_UNSUPPORTED,
+               "tc_linear: K and the row strides must be multiples of 8 elements (16-byte TMA rows)");
+  XTAG_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0, XTAG_ERR_UNSUPPORTED, "tc_linear: C must be 16-byte aligned");
+  int rc = xtag_device_check();
+  if (rc) return rc;
+  EpiParams es = {};
+  es.C = C; es.ldc = (int)ldc; es.c_is_bf16 = 1; es.alpha = 1.f; es.bias = bias;
+  return launch_tc<EPI_BIAS, false, false>(A, lda, W, (long)K, M, N, K, es, (cudaStream_t)stream);
 }
 
 extern "C" int xtag_tc_gemm_nt(const void* A, const void* B, void* C, int c_dtype, int M, int N, int K, float alpha,

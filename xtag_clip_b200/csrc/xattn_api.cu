@@ -16,7 +16,8 @@ int xattn_mma_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   cudaStream_t st);
 int xattn_mma_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                   void* dq, void* dk, void* dv, float* delta_ws, int b, int Lq, int Lk, int heads, int dh, int ldq, int ldk,
-                  int ldv, float sm_scale, float p_drop, uint64_t seed, uint64_t offset, cudaStream_t st);
+                  int ldv, int lddk, int lddv, float sm_scale, float p_drop, uint64_t seed, uint64_t offset,
+                  cudaStream_t st);
 }  // namespace xtag
 
 using namespace xtag;
@@ -58,7 +59,17 @@ extern "C" int xtag_xattn_bwd(const void* q, const void* k, const void* v, const
                               const float* lse, int dtype, void* dq, void* dk, void* dv, int b, int Lq, int Lk, int heads,
                               int dh, int ldq, int ldk, int ldv, float softmax_scale, float dropout_p, uint64_t seed,
                               uint64_t offset, void* ws, size_t ws_bytes, void* stream) {
+  return xtag_xattn_bwd_ld(q, k, v, o, d_o, lse, dtype, dq, dk, dv, b, Lq, Lk, heads, dh, ldq, ldk, ldv, heads * dh,
+                           heads * dh, softmax_scale, dropout_p, seed, offset, ws, ws_bytes, stream);
+}
+
+extern "C" int xtag_xattn_bwd_ld(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                 const float* lse, int dtype, void* dq, void* dk, void* dv, int b, int Lq, int Lk,
+                                 int heads, int dh, int ldq, int ldk, int ldv, int lddk, int lddv, float softmax_scale,
+                                 float dropout_p, uint64_t seed, uint64_t offset, void* ws, size_t ws_bytes,
+                                 void* stream) {
   XTAG_REQUIRE(q && k && v && o && d_o && lse && dq && dk && dv, XTAG_ERR_INVALID, "xattn_bwd: null pointer");
+  XTAG_REQUIRE(lddk >= heads * dh && lddv >= heads * dh, XTAG_ERR_INVALID, "xattn_bwd: dK / dV row strides too small");
   int rc = check_common("xattn_bwd", dtype, b, Lq, Lk, heads, dh, ldq, ldk, ldv, dropout_p);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -66,9 +77,12 @@ extern "C" int xtag_xattn_bwd(const void* q, const void* k, const void* v, const
   if (mma_eligible(q, k, v, dtype, Lq, dh, heads, ldq, ldk, ldv) && al(o) && al(d_o) && al(dq) && al(dk) && al(dv)) {
     XTAG_REQUIRE(ws && ws_bytes >= (size_t)b * heads * Lq * sizeof(float), XTAG_ERR_WORKSPACE,
                  "xattn_bwd: workspace of b*heads*Lq floats required");
-    return xattn_mma_bwd(q, k, v, o, d_o, lse, dq, dk, dv, (float*)ws, b, Lq, Lk, heads, dh, ldq, ldk, ldv, softmax_scale,
-                         dropout_p, seed, offset, st);
+    if (lddk % 8 == 0 && lddv % 8 == 0)
+      return xattn_mma_bwd(q, k, v, o, d_o, lse, dq, dk, dv, (float*)ws, b, Lq, Lk, heads, dh, ldq, ldk, ldv, lddk, lddv,
+                           softmax_scale, dropout_p, seed, offset, st);
   }
+  XTAG_REQUIRE(lddk == heads * dh && lddv == heads * dh, XTAG_ERR_UNSUPPORTED,
+               "xattn_bwd: strided dK / dV outputs are only supported by the bf16 tensor-core path");
   if (dtype == XTAG_F32)
     return xattn_simt_bwd<float>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, dh, ldq, ldk, ldv, softmax_scale,
                                  dropout_p, seed, offset, st);

@@ -983,7 +983,8 @@ xattn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 template <int NCH, int NW>
 static int launch_bwd_fused(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                             const float* lse, void* dq, void* dk, void* dv, int b, int Lq, int Lk, int heads, int ldq,
-                            int ldk, int ldv, float sm_scale, float p, uint64_t seed, uint64_t offset, cudaStream_t st) {
+                            int ldk, int ldv, int lddk, int lddv, float sm_scale, float p, uint64_t seed, uint64_t offset,
+                            cudaStream_t st) {
   const int dh = NCH * 64, HD = heads * dh;
   const float sl2 = sm_scale * kLog2e;
   CUtensorMap tq, tdo, tk, tv, tdk, tdv;
@@ -992,8 +993,8 @@ static int launch_bwd_fused(const void* q, const void* k, const void* v, const v
   if ((rc = xa_make_tmap(&tdo, d_o, b, Lq, HD, HD, 16 * NW))) return rc;
   if ((rc = xa_make_tmap(&tk, k, b, Lk, HD, ldk, XA_KT))) return rc;
   if ((rc = xa_make_tmap(&tv, v, b, Lk, HD, ldv, XA_KT))) return rc;
-  if ((rc = xa_make_tmap(&tdk, dk, b, Lk, HD, HD, XA_KT))) return rc;
-  if ((rc = xa_make_tmap(&tdv, dv, b, Lk, HD, HD, XA_KT))) return rc;
+  if ((rc = xa_make_tmap(&tdk, dk, b, Lk, HD, lddk, XA_KT))) return rc;      // dK / dV may be column slices of a wider
+  if ((rc = xa_make_tmap(&tdv, dv, b, Lk, HD, lddv, XA_KT))) return rc;      // buffer (row stride lddk / lddv)
   const size_t q_pad = ((size_t)NCH * 16 * NW * 128 + 1023) & ~(size_t)1023;
   const size_t smem = 1024 + 2 * q_pad + 2 * (2 * NCH * XA_KT * 128) + NCH * XA_KT * 128 + 2 * (16 * NW * 64) + 64 +
                       16 * NW * 4;
@@ -1009,13 +1010,13 @@ static int launch_bwd_fused(const void* q, const void* k, const void* v, const v
 template <int NCH>
 static int launch_bwd_fused_nch(int nw, const void* q, const void* k, const void* v, const void* o, const void* d_o,
                                 const float* lse, void* dq, void* dk, void* dv, int b, int Lq, int Lk, int heads,
-                                int ldq, int ldk, int ldv, float sm_scale, float p, uint64_t seed, uint64_t offset,
-                                cudaStream_t st) {
+                                int ldq, int ldk, int ldv, int lddk, int lddv, float sm_scale, float p, uint64_t seed,
+                                uint64_t offset, cudaStream_t st) {
   switch (nw) {
-    case 1: return launch_bwd_fused<NCH, 1>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p, seed, offset, st);
-    case 2: return launch_bwd_fused<NCH, 2>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p, seed, offset, st);
-    case 3: return launch_bwd_fused<NCH, 3>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p, seed, offset, st);
-    default: return launch_bwd_fused<NCH, 4>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p, seed, offset, st);
+    case 1: return launch_bwd_fused<NCH, 1>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, lddk, lddv, sm_scale, p, seed, offset, st);
+    case 2: return launch_bwd_fused<NCH, 2>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, lddk, lddv, sm_scale, p, seed, offset, st);
+    case 3: return launch_bwd_fused<NCH, 3>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, lddk, lddv, sm_scale, p, seed, offset, st);
+    default: return launch_bwd_fused<NCH, 4>(q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, lddk, lddv, sm_scale, p, seed, offset, st);
   }
 }
 
@@ -1069,19 +1070,22 @@ static int launch_bwd(const void* q, const void* k, const void* v, const void* o
 // delta_ws: caller scratch of b*heads*Lq floats
 int xattn_mma_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                   void* dq, void* dk, void* dv, float* delta_ws, int b, int Lq, int Lk, int heads, int dh, int ldq, int ldk,
-                  int ldv, float sm_scale, float p_drop, uint64_t seed, uint64_t offset, cudaStream_t st) {
+                  int ldv, int lddk, int lddv, float sm_scale, float p_drop, uint64_t seed, uint64_t offset,
+                  cudaStream_t st) {
   // the single-pass kernel keeps dQ [16 x dh] and one [32 x dh/NW] product tile per warp in registers: shapes whose
   // accumulators would spill (few warps with a wide head) stay on the two-kernel path
   const int nw = (Lq + 15) / 16, nch = dh / 64;
   const int acc_regs = 16 * ((nch * 4 + nw - 1) / nw) + 32 * nch;
   if ((tc_tune() & kTuneXattnFusedBwd) && acc_regs <= 224) {
     switch (nch) {
-      case 1: return launch_bwd_fused_nch<1>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
-      case 2: return launch_bwd_fused_nch<2>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
-      case 3: return launch_bwd_fused_nch<3>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
-      default: return launch_bwd_fused_nch<4>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+      case 1: return launch_bwd_fused_nch<1>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, lddk, lddv, sm_scale, p_drop, seed, offset, st);
+      case 2: return launch_bwd_fused_nch<2>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, lddk, lddv, sm_scale, p_drop, seed, offset, st);
+      case 3: return launch_bwd_fused_nch<3>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, lddk, lddv, sm_scale, p_drop, seed, offset, st);
+      default: return launch_bwd_fused_nch<4>(nw, q, k, v, o, d_o, lse, dq, dk, dv, b, Lq, Lk, heads, ldq, ldk, ldv, lddk, lddv, sm_scale, p_drop, seed, offset, st);
     }
   }
+  XTAG_REQUIRE(lddk == heads * dh && lddv == heads * dh, XTAG_ERR_UNSUPPORTED,
+               "xattn_bwd: strided dK / dV outputs need the single-pass kernel (tune bit 11, accumulators that fit)");
   switch (dh / 64) {
     case 1: return launch_bwd<1>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
     case 2: return launch_bwd<2>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);

@@ -276,6 +276,21 @@ class CudaKernels:
               "xtag_tc_gemm_nt")
         return C
 
+    def tc_linear(self, x2d: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+        """y [M, N] bf16 = x2d [M, K] bf16 @ weight [N, K]^T bf16 + bias [N] fp32 on the tcgen05 dense-layer kernel."""
+        _cuda(x2d, weight, bias)
+        assert x2d.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x2d.dim() == 2 and weight.dim() == 2
+        x2d, weight = x2d.contiguous(), weight.contiguous()
+        M, Kd = x2d.shape
+        N = weight.shape[0]
+        assert weight.shape[1] == Kd and N % 8 == 0
+        if bias is not None:
+            bias = bias.detach().to(torch.float32).contiguous()
+        y = torch.empty((M, N), dtype=torch.bfloat16, device=x2d.device)
+        check(self.lib.xtag_tc_linear_bf16(_p(x2d), Kd, _p(weight), _p(bias), _p(y), N, M, N, Kd, _stream()),
+              "xtag_tc_linear_bf16")
+        return y
+
     def tc_gemm(self, A: torch.Tensor, B: torch.Tensor, a_mn: bool, b_mn: bool, out_dtype=torch.float32,
                 alpha: float = 1.0):
         """C[M,N] = alpha * sum_k A(m,k) B(n,k); A is [M,K] (a_mn False) or [K,M] (True), B is [N,K] or [K,N]."""
@@ -284,8 +299,10 @@ class CudaKernels:
         (K, M) = A.shape if a_mn else A.shape[::-1]
         N = B.shape[1] if b_mn else B.shape[0]
         C = torch.empty((M, N), dtype=out_dtype, device=A.device)
-        check(self.lib.xtag_tc_gemm(_p(A), _p(B), _p(C), _DT[out_dtype], M, N, K, float(alpha), int(a_mn), int(b_mn),
-                                    _stream()), "xtag_tc_gemm")
+        nbytes = int(self.lib.xtag_tc_gemm_ws_bytes(M, N, K))          # split-K slabs (few output tiles, long K)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device) if nbytes else None
+        check(self.lib.xtag_tc_gemm_ex(_p(A), _p(B), _p(C), _DT[out_dtype], M, N, K, float(alpha), int(a_mn), int(b_mn),
+                                       _p(ws), nbytes, _stream()), "xtag_tc_gemm_ex")
         return C
 
     # ---- K4 ----------------------------------------------------------------------------------
@@ -306,20 +323,40 @@ class CudaKernels:
         return o, lse
 
     def xattn_bwd(self, q, k, v, o, do, lse, heads: int, softmax_scale: float, dropout_p: float, seed: int,
-                  offset: int):
-        _cuda(q, k, v, o, do, lse)
+                  offset: int, dk_out: Optional[torch.Tensor] = None, dv_out: Optional[torch.Tensor] = None):
+        """-> (dq, dk, dv).  dk_out / dv_out: write dK / dV into these [b, Lk, H] views (last dim contiguous, uniform
+        row stride -- e.g. column slices of one fused K|V gradient buffer); bf16 tensor-core path only, otherwise the
+        gradients are computed contiguously and copied in."""
+        _cuda(q, k, v, o, do, lse, dk_out, dv_out)
         b, Lq, H = q.shape
         Lk = k.shape[1]
         dh = H // heads
         do = do.contiguous()
         dq = torch.empty((b, Lq, H), dtype=q.dtype, device=q.device)
+        ws = torch.empty(b * heads * Lq, dtype=torch.float32, device=q.device)
+        strided = dk_out is not None and dv_out is not None
+        if strided:
+            for t in (dk_out, dv_out):
+                assert t.shape == (b, Lk, H) and t.dtype == q.dtype and t.stride(-1) == 1 and \
+                    t.stride(0) == Lk * t.stride(1), "dk_out / dv_out: [b, Lk, H] views with uniformly strided rows"
+            rc = self.lib.xtag_xattn_bwd_ld(_p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _dt(q), _p(dq), _p(dk_out),
+                                            _p(dv_out), b, Lq, Lk, heads, dh, q.stride(1), k.stride(1), v.stride(1),
+                                            dk_out.stride(1), dv_out.stride(1), float(softmax_scale), float(dropout_p),
+                                            int(seed), int(offset), _p(ws), ws.numel() * 4, _stream())
+            if rc == 0:
+                return dq, dk_out, dv_out
+            if rc != _lib.ERR_UNSUPPORTED:
+                check(rc, "xtag_xattn_bwd_ld")
         dk = torch.empty((b, Lk, H), dtype=q.dtype, device=q.device)
         dv = torch.empty((b, Lk, H), dtype=q.dtype, device=q.device)
-        ws = torch.empty(b * heads * Lq, dtype=torch.float32, device=q.device)
         check(self.lib.xtag_xattn_bwd(_p(q), _p(k), _p(v), _p(o), _p(do), _p(lse), _dt(q), _p(dq), _p(dk), _p(dv),
                                       b, Lq, Lk, heads, dh, q.stride(1), k.stride(1), v.stride(1),
                                       float(softmax_scale), float(dropout_p), int(seed), int(offset),
                                       _p(ws), ws.numel() * 4, _stream()), "xtag_xattn_bwd")
+        if strided:
+            dk_out.copy_(dk)
+            dv_out.copy_(dv)
+            return dq, dk_out, dv_out
         return dq, dk, dv
 
     # ---- K5 ----------------------------------------------------------------------------------

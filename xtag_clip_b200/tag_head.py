@@ -66,27 +66,100 @@ def l2_normalize(x: torch.Tensor, eps: float = 1e-12, out_dtype: Optional[torch.
 # ---- K4 -------------------------------------------------------------------------------------------
 class _CrossAttention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, heads, dropout_p, seed, offset, kernels):
+    def forward(ctx, q, k, v, heads, dropout_p, seed, offset, kernels, sink):
         K = _kernels(kernels)
         scale = 1.0 / math.sqrt(q.shape[-1] // heads)
         o, lse = K.xattn_fwd(q, k, v, heads, scale, dropout_p, seed, offset)
         ctx.save_for_backward(q, k, v, o, lse)
-        ctx.meta = (K, heads, scale, dropout_p, seed, offset)
+        ctx.meta = (K, heads, scale, dropout_p, seed, offset, sink)
         return o
 
     @staticmethod
     def backward(ctx, do):
         q, k, v, o, lse = ctx.saved_tensors
-        K, heads, scale, dropout_p, seed, offset = ctx.meta
-        dq, dk, dv = K.xattn_bwd(q, k, v, o, do, lse, heads, scale, dropout_p, seed, offset)
-        return dq, dk, dv, None, None, None, None, None
+        K, heads, scale, dropout_p, seed, offset, sink = ctx.meta
+        dk_out = dv_out = None
+        if sink is not None:
+            # k and v are column slices of ONE fused projection buffer: their gradients go straight into the matching
+            # slices of one gradient buffer, which then feeds a single projection-backward GEMM
+            dk_out, dv_out = sink[0].slices(k, sink[1], sink[2])
+        if dk_out is not None:
+            dq, dk, dv = K.xattn_bwd(q, k, v, o, do, lse, heads, scale, dropout_p, seed, offset, dk_out=dk_out,
+                                     dv_out=dv_out)
+        else:
+            dq, dk, dv = K.xattn_bwd(q, k, v, o, do, lse, heads, scale, dropout_p, seed, offset)
+        return dq, dk, dv, None, None, None, None, None, None
 
 
-def cross_attention(q, k, v, heads: int, dropout_p: float = 0.0, seed: int = 0, offset: int = 0, *, _kernels=None):
+def cross_attention(q, k, v, heads: int, dropout_p: float = 0.0, seed: int = 0, offset: int = 0, *, _kernels=None,
+                    _sink=None):
     """softmax(q k^T / sqrt(dh)) v per (sample, head) -- bert.py:219-274.  q [b,Lq,H], k/v [b,Lk,H]."""
     if q.dtype == torch.float16:          # fp16 autocast: run the exact fp32 kernel
         q, k, v = q.float(), k.float(), v.float()
-    return _CrossAttention.apply(q.contiguous(), k, v, heads, dropout_p, seed, offset, _kernels)
+    return _CrossAttention.apply(q.contiguous(), k, v, heads, dropout_p, seed, offset, _kernels, _sink)
+
+
+# ---- fused K|V projection of all layers (SURVEY.md section 8f rank 1) ------------------------------------------------
+class _KVGradBuffer:
+    """One [b, N, width] gradient buffer per tag_forward call, allocated by the first attention backward that runs;
+    every layer's K4 backward writes its dK / dV into its column slices."""
+
+    def __init__(self, width: int):
+        self.width, self.buf, self.written = width, None, set()
+
+    def slices(self, like: torch.Tensor, col_k: int, col_v: int):
+        b, n, h = like.shape
+        if self.buf is None:
+            self.buf = torch.empty((b, n, self.width), dtype=like.dtype, device=like.device)
+        self.written.update((col_k, col_v))
+        return self.buf[..., col_k:col_k + h], self.buf[..., col_v:col_v + h]
+
+
+class _FusedKVProjection(torch.autograd.Function):
+    """kv [b, N, 2*L*768] = tokens [b, N, D] @ cat(W_k0, W_v0, W_k1, W_v1)^T + cat(biases)  -- the key / value Linear
+    layers of every tagging layer (bert.py:208-209) as ONE tcgen05 GEMM with a bias epilogue (`xtag_tc_linear_bf16`);
+    the outputs are the per-layer column slices, which K4 reads in place through their row stride.
+    Backward: the slices' gradients arrive inside one buffer (`_KVGradBuffer`), so d tokens = dkv @ W and
+    dW = dkv^T @ tokens are two GEMMs on the package's own kernels with the operands read in place (MN-major
+    descriptors); d bias is a column sum."""
+
+    @staticmethod
+    def forward(ctx, tokens, weight, bias, n_out, kernels, gbuf):
+        K = _kernels(kernels)
+        b, n, d = tokens.shape
+        x2d = tokens.reshape(b * n, d)
+        wb = weight.to(torch.bfloat16)
+        kv = K.tc_linear(x2d, wb, bias).view(b, n, -1)
+        h = kv.shape[-1] // n_out
+        ctx.save_for_backward(x2d, wb)
+        ctx.meta = (K, gbuf, tokens.shape, weight.dtype, bias.dtype, n_out, h)
+        return tuple(kv[..., i * h:(i + 1) * h] for i in range(n_out))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x2d, wb = ctx.saved_tensors
+        K, gbuf, tok_shape, w_dtype, b_dtype, n_out, h = ctx.meta
+        b, n, d = tok_shape
+        buf = gbuf.buf
+        if buf is None:
+            buf = torch.empty((b, n, n_out * h), dtype=torch.bfloat16, device=x2d.device)
+        for i, g in enumerate(grads):
+            sl = buf[..., i * h:(i + 1) * h]
+            if g is None:
+                sl.zero_()
+            elif g.data_ptr() != sl.data_ptr() or g.stride() != sl.stride():
+                sl.copy_(g)                 # a gradient that did not come through the shared buffer
+        dkv = buf.view(b * n, n_out * h)
+        d_tok = d_w = d_b = None
+        if ctx.needs_input_grad[0]:
+            # d tokens [b*n, D] = dkv [b*n, K'] @ W [K', D]: W is the B operand stored [K'][D] (MN-major)
+            d_tok = K.tc_gemm(dkv, wb, False, True, torch.bfloat16).view(b, n, d)
+        if ctx.needs_input_grad[1]:
+            # dW [K', D] = dkv^T @ tokens: both operands stored [b*n rows][...]: MN-major A and B, fp32 out
+            d_w = K.tc_gemm(dkv, x2d, True, True, torch.float32).to(w_dtype)
+        if ctx.needs_input_grad[2]:
+            d_b = dkv.sum(dim=0, dtype=torch.float32).to(b_dtype)
+        return d_tok, d_w, d_b, None, None, None
 
 
 # ---- module tree with the reference's parameter names --------------------------------------------
@@ -143,8 +216,9 @@ class TagHead(nn.Module):
     ``tag_forward``.  Use ``TagHead.from_reference(model)`` / ``load_state_dict(filtered)`` to take over the
     weights of a reference ``CLIP`` and ``patch_reference_model(model)`` to route ``model.tag_forward`` here."""
 
-    def __init__(self, embed_dim: int, tag_list: Optional[List[str]] = None, *, _kernels=None):
+    def __init__(self, embed_dim: int, tag_list: Optional[List[str]] = None, *, fuse_kv: bool = True, _kernels=None):
         super().__init__()
+        self.fuse_kv = fuse_kv
         self.tag_head = _TagBert(embed_dim)
         self.tag_labels = nn.Embedding(TAG_QUERIES, TAG_HIDDEN)
         self.tag_fc = nn.Linear(TAG_HIDDEN, 1)
@@ -184,7 +258,22 @@ class TagHead(nn.Module):
         self._step += 1
         h = None                                   # layer-0 hidden state is the shared label embedding
         label = self.tag_labels.weight             # [44, 768]
-        for li, layer in enumerate(self.tag_head.encoder.layer):
+        layers = list(self.tag_head.encoder.layer)
+        # bf16 on the GPU (the reference's amp_bf16 training): key and value projections of ALL layers as one
+        # [b*N, D] x [D, 2*L*768] GEMM with a bias epilogue on the package's own tcgen05 kernel; K4 reads the per-layer
+        # column slices in place.  fp32 (exact mode) keeps one library Linear per projection.
+        amp_bf16 = tag_embeds.is_cuda and torch.is_autocast_enabled("cuda") and \
+            torch.get_autocast_dtype("cuda") == torch.bfloat16
+        fused_kv = None
+        if self.fuse_kv and tag_embeds.is_cuda and self.embed_dim % 8 == 0 and \
+                (tag_embeds.dtype == torch.bfloat16 or amp_bf16) and \
+                hasattr(_kernels(self._k), "tc_linear"):
+            w = torch.cat([m.weight for l in layers for m in (l.crossattention.self.key, l.crossattention.self.value)], 0)
+            bcat = torch.cat([m.bias for l in layers for m in (l.crossattention.self.key, l.crossattention.self.value)], 0)
+            gbuf = _KVGradBuffer(2 * len(layers) * TAG_HIDDEN)
+            fused_kv = (_FusedKVProjection.apply(tag_embeds.to(torch.bfloat16).contiguous(), w, bcat, 2 * len(layers),
+                                                 self._k, gbuf), gbuf)
+        for li, layer in enumerate(layers):
             ca = layer.crossattention
             if h is None:
                 q = ca.self.query(label).unsqueeze(0).expand(bs, -1, -1)     # once, not per sample
@@ -192,9 +281,15 @@ class TagHead(nn.Module):
             else:
                 q = ca.self.query(h)
                 resid = h
-            k = ca.self.key(tag_embeds)
-            v = ca.self.value(tag_embeds)
-            ctx = cross_attention(q, k, v, TAG_HEADS, drop, seed, self._step * TAG_LAYERS + li, _kernels=self._k)
+            if fused_kv is not None:
+                k, v = fused_kv[0][2 * li], fused_kv[0][2 * li + 1]
+                sink = (fused_kv[1], 2 * li * TAG_HIDDEN, (2 * li + 1) * TAG_HIDDEN)
+                ctx = cross_attention(q.to(k.dtype), k, v, TAG_HEADS, drop, seed, self._step * TAG_LAYERS + li,
+                                      _kernels=self._k, _sink=sink)
+            else:
+                k = ca.self.key(tag_embeds)
+                v = ca.self.value(tag_embeds)
+                ctx = cross_attention(q, k, v, TAG_HEADS, drop, seed, self._step * TAG_LAYERS + li, _kernels=self._k)
             a = F.dropout(ca.output.dense(ctx.to(k.dtype)), drop, self.training)
             a = ca.output.LayerNorm(a + resid)
             f = F.gelu(layer.intermediate.dense(a))
@@ -234,6 +329,7 @@ def patch_reference_model(model: nn.Module, *, _kernels=None) -> nn.Module:
     head.embed_dim = model.tag_head.encoder.layer[0].crossattention.self.key.weight.shape[1]
     head.tag_list = getattr(model, "tag_list", None)
     head._k, head._step = _kernels, 0
+    head.fuse_kv = True
 
     def tag_forward(tag_embeds):
         head.__dict__["training"] = model.training
