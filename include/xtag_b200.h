@@ -261,6 +261,18 @@ int xtag_debug_tile_coords(int M, int N, int slab, const int* order_host, int ti
                            int* m_blk, int* n_blk, int* slab_idx);
 int xtag_debug_pick_cluster(int M, int N, int tune);
 
+/* ---- symmetric cross-entropy on a materialised square score matrix: DQNCOSLoss of the TQN fusion head ---------
+ * (reference src/open_clip/tagging_heads/asymmetric_loss.py:54-65;  SURVEY.md section 8f rank 2)
+ *   loss = 0.5 * [ mean_i(LSE_j X_ij - X_ii) + mean_j(LSE_i X_ij - X_jj) ],  X [n, n] fp32 or bf16, row stride ld
+ *   dX   = grad_out * ( softmax_row(X) + softmax_col(X) - 2 I ) / (2 n)
+ * fwd reads X once (row_lse, col_lse, diag [n] fp32 natural log are kept for bwd; ws = xtag_symm_ce_ws_bytes(n));
+ * bwd reads X once and writes dX (same dtype as X, row stride lddx).  grad_out is a DEVICE scalar. */
+size_t xtag_symm_ce_ws_bytes(int n);
+int xtag_symm_ce_fwd(const void* x, int dtype, int n, long ld, float* row_lse, float* col_lse, float* diag,
+                     float* loss_out, void* ws, size_t ws_bytes, void* stream);
+int xtag_symm_ce_bwd(const void* x, int dtype, int n, long ld, const float* row_lse, const float* col_lse,
+                     const float* grad_out, void* dx, long lddx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -163,3 +163,22 @@ def test_dqn_cos_loss_gpu(G):
         l.backward()
         assert abs(float(l) - float(G[f"ce{n}_loss"])) <= 1e-5 * max(1.0, abs(float(G[f"ce{n}_loss"])))
         assert rel_err(x.grad, G[f"ce{n}_dx"]) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,dtype", [(7, torch.float32), (130, torch.float32), (1024, torch.bfloat16), (333, torch.bfloat16)])
+def test_symm_ce_kernels_gpu(n, dtype):
+    """csrc/symm_ce.cu against the oracle's DQNCOSLoss on random matrices with a wide range (|x| up to ~60), ragged
+    sizes and a strided (non-contiguous rows) input."""
+    g = torch.Generator().manual_seed(n)
+    big = torch.randn(n, n + 8, generator=g) * 20
+    x = big[:, :n].to(dtype).cuda().requires_grad_(True)               # row stride n + 8 after .cuda()? keep it strided:
+    xs = big.to(dtype).cuda()[:, :n].detach().requires_grad_(True)
+    for inp in (x, xs):
+        loss = xt.DQNCOSLoss()(inp)
+        (loss * 1.7).backward()
+        x64 = inp.detach().double().cpu().requires_grad_(True)
+        ref = oracle.dqn_cos_loss(x64)
+        (ref * 1.7).backward()
+        assert abs(float(loss) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref)))
+        assert rel_err(inp.grad.float(), x64.grad) < (1e-5 if dtype == torch.float32 else 6e-3)

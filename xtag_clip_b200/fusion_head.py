@@ -11,8 +11,9 @@ with `--use-fusion`.  HOST COMPOSITION over kerne
   * `fusion_scores` is model.py:552-561: memory = [mean token | tokens] of one modality, queries = the per-sample mean
     tokens of the other, output squeezed to the B x B matrix `i2t_cls` / `t2i_cls`.
   * `DQNCOSLoss` mirrors tagging_heads/asymmetric_loss.py:54-65: (CE(X, arange) + CE(X^T, arange)) / 2 on a
-    materialised B x B matrix; the row / column log-sum-exps come from `xtag_lse_reduce_log2`, the backward is the
-    closed form (softmax_row + softmax_col - 2 I) / (2B).
+    materialised B x B matrix, on its own kernels (`csrc/symm_ce.cu`): the forward reads X once (row LSEs per 32-row
+    strip, column partials finished by the shared LSE reduction), the backward is one pass that writes the closed form
+    (softmax_row + softmax_col - 2 I) / (2B).
 
 Status: host logic and parity are covered on CPU against fixtures the reference produced (tests/golden/fusion.npz);
 the GPU tests of this module (tests/test_fusion_head.py, `-m gpu`) pass on a B200.
@@ -159,6 +160,14 @@ class _SymmetricCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernels):
         K = _kernels(kernels)
+        ctx.fused = hasattr(K, "symm_ce_fwd") and x.dtype in (torch.float32, torch.bfloat16)
+        if ctx.fused:
+            # one pass over X forward (xtag_symm_ce_fwd), one pass backward (xtag_symm_ce_bwd)
+            xc = x.detach() if x.stride(-1) == 1 else x.detach().contiguous()
+            loss, row_lse, col_lse = K.symm_ce_fwd(xc)
+            ctx.K = K
+            ctx.save_for_backward(xc, row_lse, col_lse)
+            return loss
         xs = x.detach().float() * _LOG2E                                      # log2-domain copy, [B, B]
         col_lse = K.lse_reduce_log2(xs)                                       # ln sum_i exp(x_ij)
         row_lse = K.lse_reduce_log2(xs.t().contiguous())                      # ln sum_j exp(x_ij)
@@ -169,6 +178,8 @@ class _SymmetricCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, row_lse, col_lse = ctx.saved_tensors
+        if ctx.fused:
+            return ctx.K.symm_ce_bwd(x, row_lse, col_lse, g), None
         n = x.shape[0]
         xf = x.float()
         dx = torch.exp(xf - row_lse[:, None]) + torch.exp(xf - col_lse[None, :])

@@ -359,6 +359,30 @@ class CudaKernels:
             return dq, dk_out, dv_out
         return dq, dk, dv
 
+    # ---- symmetric CE on a materialised square matrix (DQNCOSLoss) ---------------------------------------
+    def symm_ce_fwd(self, x: torch.Tensor):
+        """x [n, n] (fp32 / bf16, last dim contiguous) -> (loss 0-d fp32, row_lse [n], col_lse [n]); X is read once."""
+        _cuda(x)
+        assert x.dim() == 2 and x.shape[0] == x.shape[1] and x.stride(1) == 1
+        n = x.shape[0]
+        dev = x.device
+        row, col, diag = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        nbytes = int(self.lib.xtag_symm_ce_ws_bytes(n))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(self.lib.xtag_symm_ce_fwd(_p(x), _dt(x), n, x.stride(0), _p(row), _p(col), _p(diag), _p(loss), _p(ws), nbytes,
+                                        _stream()), "xtag_symm_ce_fwd")
+        return loss, row, col
+
+    def symm_ce_bwd(self, x: torch.Tensor, row_lse: torch.Tensor, col_lse: torch.Tensor, grad_out: torch.Tensor):
+        _cuda(x, row_lse, col_lse, grad_out)
+        n = x.shape[0]
+        g = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        dx = torch.empty((n, n), dtype=x.dtype, device=x.device)
+        check(self.lib.xtag_symm_ce_bwd(_p(x), _dt(x), n, x.stride(0), _p(row_lse), _p(col_lse), _p(g), _p(dx), n,
+                                        _stream()), "xtag_symm_ce_bwd")
+        return dx
+
     # ---- K5 ----------------------------------------------------------------------------------
     def asl(self, x: torch.Tensor, y: torch.Tensor, gamma_neg, gamma_pos, clip, eps, want_dx: bool,
             want_idx: bool):
