@@ -165,6 +165,7 @@ class _Cfg:
     pull_streams: int = 1
     exchange: str = "pull"
     will_backward: bool = True       # a backward of this forward is expected (grad mode on, some input requires grad)
+    gather_buf: Optional[torch.Tensor] = None   # captured steps: the symmetric gather buffer (symm.make_graph_gather)
 
 
 def _as_scale_tensor(logit_scale, device) -> torch.Tensor:
@@ -190,8 +191,11 @@ class _FusedClipLoss(torch.autograd.Function):
             # performance mode: chunk-pipelined gather, K1 runs on column block k while block k+1 is in flight
             off = b * r
             B = b * W
-            txt_all = torch.empty((B, txt.shape[1]), dtype=txt.dtype, device=txt.device)
             sx = cfg.comm.symm_exchange(txt) if cfg.symm else None
+            if cfg.gather_buf is not None and sx is not None and tuple(cfg.gather_buf.shape) == (B, txt.shape[1]):
+                txt_all = cfg.gather_buf
+            else:
+                txt_all = torch.empty((B, txt.shape[1]), dtype=txt.dtype, device=txt.device)
             streamed = (sx is not None and cfg.stream_fwd and hasattr(K, "supports_fwd_stream")
                         and K.supports_fwd_stream(img, b, W))
             if streamed:
@@ -429,7 +433,19 @@ class _GraphedStep:
         dev = img.device
         self.cfg = cfg
         self.s_img = img.detach().clone().requires_grad_(img.requires_grad)
-        self.s_txt = txt.detach().clone().requires_grad_(txt.requires_grad)
+        self.s_txt = None
+        if (cfg.world_size > 1 and cfg.local_loss and cfg.gather_with_grad and cfg.pipeline and cfg.symm
+                and cfg.stream_fwd and cfg.exchange == "pull"):
+            # the captured step's gather buffer lives in symmetric memory; its own block is the text input slot
+            sx = cfg.comm.symm_exchange(txt)
+            if sx is not None and hasattr(sx, "make_graph_gather") and hasattr(cfg.kernels, "supports_fwd_stream") \
+                    and cfg.kernels.supports_fwd_stream(img, img.shape[0], cfg.world_size):
+                cfg.gather_buf = sx.make_graph_gather()
+                self.s_txt = sx.own_block(cfg.gather_buf).detach()
+                self.s_txt.copy_(txt.detach())
+                self.s_txt.requires_grad_(txt.requires_grad)
+        if self.s_txt is None:
+            self.s_txt = txt.detach().clone().requires_grad_(txt.requires_grad)
         self.scale_is_tensor = torch.is_tensor(logit_scale)
         if self.scale_is_tensor:
             self.s_scale = logit_scale.detach().clone().to(dev).requires_grad_(logit_scale.requires_grad)

@@ -78,6 +78,8 @@ class SymmExchange:
         self._streamed_two = False        # the last streamed gather forked the second copy stream
         self._pushed = False              # the push exchange is in use (its backward ends with a slot-release barrier)
         self.gbuf = None                  # push exchange: peer-writable gather buffers, allocated on first use
+        self.gg = None                    # captured steps: ONE symmetric gather buffer [B, D] (make_graph_gather)
+        self.peer_gg = None
 
     # ---- schedule ---------------------------------------------------------------------------------------------
     def _blocks(self) -> List[Tuple[int, int, List[int]]]:
@@ -93,6 +95,24 @@ class SymmExchange:
             g = (g0 - j) % NG
             out.append((g * G, g * G + G, list(range(g * G, g * G + G))))
         return out
+
+    # ---- captured steps: the gather buffer itself lives in symmetric memory -----------------------------------
+    def make_graph_gather(self) -> torch.Tensor:
+        """A CUDA-graph replay uses one fixed gather buffer anyway, so for captured steps it is allocated in symmetric
+        memory: the rank's own block of it doubles as the text-feature INPUT SLOT of the step (the producer writes its
+        features there) and as the source the peers pull from -- no own-block copies at all (two 8 MiB copies per
+        step at config 5 / 8 GPUs otherwise).  Safe with a single buffer: a rank overwrites its own block for step
+        t+1 only after its step-t backward, and every peer finished pulling that block before this rank could pass
+        step t's column-LSE barrier.  Collective: every rank calls it at the same point."""
+        if self.gg is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.gg = symm_mem.empty((self.B, self.D), dtype=self.feat_dtype, device=self.feat.device)
+            self.h_gg = symm_mem.rendezvous(self.gg, self._grp)
+            self.peer_gg = [self.h_gg.get_buffer(p, (self.B, self.D), self.feat_dtype) for p in range(self.W)]
+        return self.gg
+
+    def own_block(self, buf: torch.Tensor) -> torch.Tensor:
+        return buf[self.r * self.b:(self.r + 1) * self.b]
 
     # ---- forward: feature gather ------------------------------------------------------------------------------
     def begin_step(self):
@@ -138,12 +158,16 @@ class SymmExchange:
         order: it waits per block)."""
         b, s, W, r = self.b, self.slot, self.W, self.r
         cur = torch.cuda.current_stream()
-        out_all[r * b:(r + 1) * b].copy_(x)
+        unified = self.gg is not None and out_all.data_ptr() == self.gg.data_ptr()
+        if x.data_ptr() != out_all[r * b:(r + 1) * b].data_ptr():
+            out_all[r * b:(r + 1) * b].copy_(x)             # (skipped when the features were produced in the slot)
         self.s1.wait_stream(cur)
         order = [(r + j) % W for j in range(W)]
+        src = (lambda p: self.peer_gg[p][p * b:(p + 1) * b]) if unified else (lambda p: self.peer_feat[p][s])
         with torch.cuda.stream(self.s1):
-            self.feat[s].copy_(x)
-            self.h_feat.barrier(channel=0)                  # every rank's slot s is written
+            if not unified:
+                self.feat[s].copy_(x)
+            self.h_feat.barrier(channel=0)                  # every rank's block of this step is in place
         streams = [self.s1]
         if pull_streams >= 2 and W > 2:
             ready = torch.cuda.Event()
@@ -152,7 +176,7 @@ class SymmExchange:
             streams.append(self.s2)
         for k, p in enumerate(order[1:]):
             with torch.cuda.stream(streams[k % len(streams)]):
-                out_all[p * b:(p + 1) * b].copy_(self.peer_feat[p][s], non_blocking=True)
+                out_all[p * b:(p + 1) * b].copy_(src(p), non_blocking=True)
                 self.flags[p:p + 1].copy_(self.epoch, non_blocking=True)
         self._streamed_two = len(streams) == 2
         return order, [False] + [True] * (W - 1)
