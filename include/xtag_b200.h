@@ -155,9 +155,13 @@ int xtag_lse_combine(const float* parts, int W, int N, float* out, void* stream)
 int xtag_lse_combine_ptrs(const float* const* parts_dev, int W, int N, float* out, void* stream);
 /* xtag_lse_combine_ptrs + xtag_clip_loss (+ the epoch bump of the flag-gated forward) in one launch: col_out [N] =
  * combined column LSEs; loss_out[0] = this rank's loss over its M rows / label columns [label_offset, label_offset+M);
- * epoch (device int, may be NULL) is incremented once, for the next forward. */
+ * epoch (device int, may be NULL) is incremented once, for the next forward.  scratch: device buffer of
+ * xtag_lse_combine_loss_scratch_bytes() bytes, zero-initialised ONCE by the caller and then owned by these launches
+ * (per-block partials + a ticket that the last block resets). */
+size_t xtag_lse_combine_loss_scratch_bytes(void);
 int xtag_lse_combine_ptrs_loss(const float* const* parts_dev, int W, int N, float* col_out, const float* row_lse,
-                               const float* diag, int M, int label_offset, float* loss_out, int* epoch, void* stream);
+                               const float* diag, int M, int label_offset, float* loss_out, int* epoch,
+                               void* scratch, void* stream);
 int xtag_sum_ptrs_bf16(const void* const* parts_dev, int W, size_t n, void* out, void* stream);
 
 /* loss = 0.5 * [ mean_i(row_lse_i - diag_i) + mean_i(col_lse[label_offset+i] - diag_i) ]

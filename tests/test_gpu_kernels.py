@@ -478,6 +478,10 @@ def test_lse_reduce2_and_combine_loss(K):
     cref = torch.logsumexp(torch.stack(parts).double(), dim=0)
     lref = 0.5 * (row.double() + cref[off:off + M] - 2 * diag.double()).mean()
     assert rel_err(col, cref) < 1e-6 and abs(float(loss) - float(lref)) < 1e-5 * abs(float(lref)) and int(epoch) == 42
+    scratch = torch.zeros(K.combine_loss_scratch_bytes(), dtype=torch.uint8, device="cuda")
+    for rep in range(3):                  # the last block resets the ticket: the same scratch serves every launch
+        col2, loss2 = K.lse_combine_ptrs_loss(ptrs, W, N, row, diag, off, epoch, scratch)
+        assert torch.equal(col2, col) and float(loss2) == float(loss) and int(epoch) == 43 + rep
     assert rel_err(K.lse_combine_ptrs(ptrs, W, N), cref) < 1e-6
 
 

@@ -41,8 +41,9 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "xtag_lse_reduce_log2": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "xtag_lse_reduce2_log2": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "xtag_lse_combine_loss_scratch_bytes": (c_size_t, []),
     "xtag_lse_combine_ptrs_loss": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                           c_void_p, c_void_p, c_void_p]),
+                                           c_void_p, c_void_p, c_void_p, c_void_p]),
     "xtag_lse_combine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "xtag_lse_combine_ptrs": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "xtag_sum_ptrs_bf16": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p]),

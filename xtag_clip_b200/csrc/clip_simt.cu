@@ -395,17 +395,24 @@ __global__ void __launch_bounds__(256) lse_combine_ptrs_kernel(const float* cons
   }
 }
 
-// Column-LSE combine over the W peer buffers + this rank's loss + the exchange epoch bump, in ONE launch.  Blocks
-// [0, gridDim.x - 1) combine all n columns; the LAST block recomputes the combine for the rank's own M label columns
-// (W loads each) and reduces  0.5 * mean_i(row_lse_i + col_lse[off + i] - 2 diag_i)  in fp64, so no block waits for
-// another.  epoch (optional) is the device counter of the flag-gated forward: bumped here, at the end of a forward,
-// for the next one.
+// Column-LSE combine over the W peer buffers + this rank's loss + the exchange epoch bump, in ONE launch.  Every block
+// combines its columns (each thread reads the W peer values of one column: coalesced, all loads independent); the
+// columns that are this rank's labels [label_offset, label_offset + M) also contribute
+//   row_lse_i + col_lse[off + i] - 2 diag_i   to a per-block fp64 partial.  The blocks publish their partials in
+// `scratch` and take a ticket; the last one sums them IN BLOCK ORDER (deterministic), writes the loss, bumps the epoch
+// and resets the ticket.  scratch: 8 bytes ticket + gridDim.x doubles, zero-initialised once by the caller.
+// (A first version let one extra block re-read its M label columns from the peers: 16 dependent rounds of NVLink loads
+// per thread -- 215 us at 8 GPUs.)
 __global__ void __launch_bounds__(256) lse_combine_loss_kernel(const float* const* __restrict__ parts, int W, int n,
                                                                float* __restrict__ out,
                                                                const float* __restrict__ row_lse,
                                                                const float* __restrict__ diag, int M, int label_offset,
-                                                               float* __restrict__ loss_out, int* __restrict__ epoch) {
-  auto combine = [&](int i) {
+                                                               float* __restrict__ loss_out, int* __restrict__ epoch,
+                                                               unsigned long long* __restrict__ scratch) {
+  __shared__ double red[8];
+  __shared__ bool last;
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     float v[16];
     float mx = -INFINITY;
     for (int w = 0; w < W; ++w) {
@@ -414,25 +421,31 @@ __global__ void __launch_bounds__(256) lse_combine_loss_kernel(const float* cons
     }
     float l = 0.f;
     for (int w = 0; w < W; ++w) l += exp2f(v[w] - mx);
-    return (mx + log2f(l)) * kLn2;
-  };
-  if (blockIdx.x + 1 < gridDim.x) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (gridDim.x - 1) * blockDim.x) out[i] = combine(i);
-    return;
+    const float c = (mx + log2f(l)) * kLn2;
+    out[i] = c;
+    const int r = i - label_offset;
+    if (r >= 0 && r < M) s += (double)row_lse[r] + (double)c - 2.0 * (double)diag[r];
   }
-  __shared__ double red[8];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < M; i += blockDim.x)
-    s += (double)row_lse[i] + (double)combine(label_offset + i) - 2.0 * (double)diag[i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
+  double* partials = reinterpret_cast<double*>(scratch + 1);
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int k = 0; k < 8; ++k) t += red[k];
+    partials[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(scratch, 1ull) == (unsigned long long)(gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double t = 0.0;
+    for (unsigned k = 0; k < gridDim.x; ++k) t += reinterpret_cast<volatile double*>(partials)[k];
     loss_out[0] = (float)(0.5 * t / (double)M);
     if (epoch) epoch[0] += 1;
+    scratch[0] = 0ull;                      // ready for the next launch
   }
 }
 
@@ -473,16 +486,20 @@ extern "C" int xtag_lse_combine_ptrs(const float* const* parts_dev, int W, int N
   return XTAG_OK;
 }
 
+extern "C" size_t xtag_lse_combine_loss_scratch_bytes(void) { return 8 + 1024 * sizeof(double); }
+
 extern "C" int xtag_lse_combine_ptrs_loss(const float* const* parts_dev, int W, int N, float* col_out,
                                           const float* row_lse, const float* diag, int M, int label_offset,
-                                          float* loss_out, int* epoch, void* stream) {
-  XTAG_REQUIRE(parts_dev && col_out && row_lse && diag && loss_out && W > 0 && W <= 16 && N > 0 && M > 0 &&
+                                          float* loss_out, int* epoch, void* scratch, void* stream) {
+  XTAG_REQUIRE(parts_dev && col_out && row_lse && diag && loss_out && scratch && W > 0 && W <= 16 && N > 0 && M > 0 &&
                    label_offset >= 0 && (long)label_offset + M <= (long)N,
                XTAG_ERR_INVALID, "lse_combine_ptrs_loss: bad arguments");
   int blocks = (N + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
   if (blocks > num_sms() * 4) blocks = num_sms() * 4;
-  lse_combine_loss_kernel<<<blocks + 1, 256, 0, (cudaStream_t)stream>>>(parts_dev, W, N, col_out, row_lse, diag, M,
-                                                                       label_offset, loss_out, epoch);
+  lse_combine_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(parts_dev, W, N, col_out, row_lse, diag, M,
+                                                                   label_offset, loss_out, epoch,
+                                                                   (unsigned long long*)scratch);
   XTAG_CHECK_LAUNCH();
   return XTAG_OK;
 }

@@ -208,16 +208,24 @@ class CudaKernels:
         return out
 
     def lse_combine_ptrs_loss(self, ptrs_dev: torch.Tensor, W: int, N: int, row_lse: torch.Tensor, diag: torch.Tensor,
-                              label_offset: int, epoch: Optional[torch.Tensor] = None):
+                              label_offset: int, epoch: Optional[torch.Tensor] = None,
+                              scratch: Optional[torch.Tensor] = None):
         """-> (col_lse [N], loss 0-d): combine of the W peer buffers, this rank's loss and (optionally) the bump of the
-        exchange epoch in one launch."""
-        _cuda(ptrs_dev, row_lse, diag, epoch)
-        out = torch.empty(N, dtype=torch.float32, device=ptrs_dev.device)
-        loss = torch.empty((), dtype=torch.float32, device=ptrs_dev.device)
+        exchange epoch in one launch.  scratch: a persistent zero-initialised uint8 buffer of
+        `combine_loss_scratch_bytes()` (one per exchange object); a fresh one is made when omitted."""
+        _cuda(ptrs_dev, row_lse, diag, epoch, scratch)
+        dev = ptrs_dev.device
+        if scratch is None:
+            scratch = torch.zeros(self.combine_loss_scratch_bytes(), dtype=torch.uint8, device=dev)
+        out = torch.empty(N, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
         check(self.lib.xtag_lse_combine_ptrs_loss(_p(ptrs_dev), W, N, _p(out), _p(row_lse), _p(diag), row_lse.numel(),
-                                                  int(label_offset), _p(loss), _p(epoch), _stream()),
+                                                  int(label_offset), _p(loss), _p(epoch), _p(scratch), _stream()),
               "xtag_lse_combine_ptrs_loss")
         return out, loss
+
+    def combine_loss_scratch_bytes(self) -> int:
+        return int(self.lib.xtag_lse_combine_loss_scratch_bytes())
 
     def sum_ptrs_bf16(self, ptrs_dev: torch.Tensor, W: int, shape) -> torch.Tensor:
         _cuda(ptrs_dev)

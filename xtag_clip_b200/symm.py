@@ -78,6 +78,7 @@ class SymmExchange:
         self._streamed_two = False        # the last streamed gather forked the second copy stream
         self._pushed = False              # the push exchange is in use (its backward ends with a slot-release barrier)
         self.gbuf = None                  # push exchange: peer-writable gather buffers, allocated on first use
+        self._loss_scratch = None         # ticket + partials of the fused combine + loss kernel
         self.gg = None                    # captured steps: ONE symmetric gather buffer [B, D] (make_graph_gather)
         self.peer_gg = None
 
@@ -267,8 +268,11 @@ class SymmExchange:
         exchange epoch for the next step.  -> (col_lse, loss)"""
         self.h_col.barrier(channel=1)
         if hasattr(K, "lse_combine_ptrs_loss"):
+            if self._loss_scratch is None:
+                self._loss_scratch = torch.zeros(K.combine_loss_scratch_bytes(), dtype=torch.uint8,
+                                                 device=self.feat.device)
             return K.lse_combine_ptrs_loss(self.col_ptrs[self.slot], self.W, self.B, row_lse, diag, label_offset,
-                                           self.epoch if streamed else None)
+                                           self.epoch if streamed else None, self._loss_scratch)
         col = K.lse_combine_ptrs(self.col_ptrs[self.slot], self.W, self.B)
         if streamed:
             self.epoch.add_(1)
