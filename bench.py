@@ -353,9 +353,34 @@ def config_subrecords(dev, world, rank):
                 asl(logits.float(), y).backward()
 
             ms = _time_steps(step_head, iters=10, warmup=3)
+            # the same head on stock PyTorch ops only (the reference's formulation: one Linear per projection, eager
+            # softmax attention with its [b, 4, 44, N] score tensor, separate dropout / add / LayerNorm kernels)
+            import math
+            import torch.nn.functional as F
+            from xtag_clip_b200 import tag_head as th
+
+            def eager_attention(q, k, v, heads, dropout_p=0.0, seed=0, offset=0, **kw):
+                bb, Lq, H = q.shape
+                dh = H // heads
+                qh = q.reshape(bb, Lq, heads, dh).permute(0, 2, 1, 3)
+                kh = k.reshape(bb, -1, heads, dh).permute(0, 2, 1, 3)
+                vh = v.reshape(bb, -1, heads, dh).permute(0, 2, 1, 3)
+                pr = torch.softmax((qh @ kh.transpose(-1, -2)) / math.sqrt(dh), dim=-1)
+                pr = F.dropout(pr, dropout_p, dropout_p > 0)
+                return (pr @ vh).permute(0, 2, 1, 3).reshape(bb, Lq, H)
+
+            orig, flags = th.cross_attention, (head.fuse_kv, head.fuse_ln)
+            th.cross_attention, head.fuse_kv, head.fuse_ln = eager_attention, False, False
+            try:
+                ms_lib = _time_steps(step_head, iters=10, warmup=3)
+            finally:
+                th.cross_attention = orig
+                head.fuse_kv, head.fuse_ln = flags
             out["C3_tag_head_fwd_bwd_train_bf16"] = dict(b=b, N=N, D=D, ms_per_step=ms, samples_per_s=b / ms * 1e3,
+                                                         torch_b200_ms_per_step=ms_lib, speedup_vs_torch_b200=ms_lib / ms,
                                                          what="TagHead.tag_forward (2 cross-attention layers, dropout 0.1)"
-                                                              " + AsymmetricLoss, fwd+bwd, bf16 autocast")
+                                                              " + AsymmetricLoss, fwd+bwd, bf16 autocast; torch_b200 = the "
+                                                              "same head on stock PyTorch ops only, same GPU")
         except Exception as e:
             out["C3_tag_head_fwd_bwd_train_bf16"] = dict(error=f"{type(e).__name__}: {e}"[:200])
     else:

@@ -277,6 +277,22 @@ int xtag_symm_ce_fwd(const void* x, int dtype, int n, long ld, float* row_lse, f
 int xtag_symm_ce_bwd(const void* x, int dtype, int n, long ld, const float* row_lse, const float* col_lse,
                      const float* grad_out, void* dx, long lddx, void* stream);
 
+/* ---- K6: dense-output block of the tag head's BERT layers, fused ----------------------------------------------
+ * (reference src/open_clip/tagging_heads/bert.py:281-292 BertSelfOutput, :359-370 BertOutput)
+ *   y = LayerNorm( dropout(x) + resid[r % resid_rows] ) * gamma + beta          x, z, y bf16 [rows, H]; H in {256..1024}
+ * fwd: one pass; keeps z (the pre-normalisation sum, bf16), mean and rstd [rows] fp32 for the backward.
+ * bwd: one pass over dy (fp32 or bf16) and z -> dx, dresid (bf16 [rows, H]; the caller sums dresid over the samples
+ *      when resid was broadcast), dgamma | dbeta as ONE [2, H] fp32 buffer (dbeta == dgamma + H).
+ * The dropout keep-mask is Philox4x32-7 keyed by (seed, offset, element index): statistically equivalent to
+ * torch.nn.Dropout, not bit-identical; dropout_p == 0 is eval mode. */
+size_t xtag_ln_res_bwd_ws_bytes(int rows, int H);
+int xtag_ln_res_fwd(const void* x, const void* resid, int resid_dtype, int resid_rows, const float* gamma,
+                    const float* beta, void* z, void* y, float* mean, float* rstd, int rows, int H, float eps,
+                    float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+int xtag_ln_res_bwd(const void* dy, int dy_dtype, const void* z, const float* mean, const float* rstd,
+                    const float* gamma, void* dx, void* dresid, float* dgamma, float* dbeta, int rows, int H,
+                    float dropout_p, uint64_t seed, uint64_t offset, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,7 +174,7 @@ def test_tag_head_bf16_config3_full_batch_fwd_bwd():
     Linear per projection) on the full batch."""
     D, b, N, ns = 512, 1024, 197, 32
     params = make_tag_params(11, D, gain=4.0, dtype=torch.float32)
-    heads = [xt.TagHead(D, fuse_kv=f).cuda() for f in (True, False)]
+    heads = [xt.TagHead(D).cuda(), xt.TagHead(D, fuse_kv=False, fuse_ln=False).cuda()]     # production / library path
     for h in heads:
         h.load_state_dict(params, strict=True)
         h.eval()
@@ -189,9 +189,12 @@ def test_tag_head_bf16_config3_full_batch_fwd_bwd():
         (logits.float() * wgt.cuda()).sum().backward()
         kw = h.tag_head.encoder.layer[1].crossattention.self.key.weight.grad
         vb = h.tag_head.encoder.layer[0].crossattention.self.value.bias.grad
-        outs.append((logits.float().detach(), tok.grad.detach(), kw.detach().clone(), vb.detach().clone()))
-    for a, c, tol in zip(outs[0], outs[1], (4e-2, 4e-2, 4e-2, 4e-2)):    # two bf16 pipelines, max-norm
-        assert rel_err(a, c) < tol, rel_err(a, c)
+        lw = h.tag_head.encoder.layer[0].crossattention.output.LayerNorm.weight.grad
+        lb = h.tag_head.encoder.layer[1].output.LayerNorm.bias.grad
+        outs.append((logits.float().detach(), tok.grad.detach(), kw.detach().clone(), vb.detach().clone(),
+                     lw.detach().clone(), lb.detach().clone(), h.tag_labels.weight.grad.detach().clone()))
+    for a, c in zip(outs[0], outs[1]):                                   # two bf16 pipelines, max-norm
+        assert rel_err(a, c) < 4e-2, rel_err(a, c)
     p64 = {k: v.double() for k, v in params.items()}
     tok64 = tokens[:ns].double().requires_grad_(True)
     ref = oracle.tag_head_forward(tok64, p64)

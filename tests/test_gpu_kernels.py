@@ -541,3 +541,43 @@ def test_tc_gemm_split_k(K, M, N, Kd, a_mn, b_mn):
         assert rel_err(K.tc_gemm(Aop, Bop, a_mn, b_mn, torch.float32), ref) < 2e-5
     finally:
         K.lib.xtag_set_tune(old)
+
+
+@pytest.mark.parametrize("rows,H,rr,rdt", [(44 * 9, 768, 44, torch.float32), (1000, 768, 1000, torch.bfloat16),
+                                            (37, 256, 37, torch.bfloat16), (64, 1024, 64, torch.float32)])
+def test_ln_res_fused(K, rows, H, rr, rdt):
+    """K6: y = LayerNorm(dropout(x) + resid) (bert.py:281-292, 359-370) forward and backward against torch autograd in
+    fp32 on the same bf16 inputs (eval mode, incl. the broadcast residual of layer 0), then the dropout path: keep rate,
+    scaling, and a backward that regenerates exactly the forward's mask."""
+    g = torch.Generator().manual_seed(rows + H)
+    x = torch.randn(rows, H, generator=g).bfloat16().cuda()
+    resid = (torch.randn(rr, H, generator=g) * 0.5).to(rdt).cuda()
+    gamma = (1 + 0.1 * torch.randn(H, generator=g)).cuda()
+    beta = (0.1 * torch.randn(H, generator=g)).cuda()
+    dy = torch.randn(rows, H, generator=g).cuda()
+    y, z, mean, rstd = K.ln_res_fwd(x, resid, gamma, beta, 1e-12, 0.0, 1, 2)
+    xr = x.float().requires_grad_(True)
+    rr_ = resid.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    zz = xr + rr_.repeat(rows // rr, 1)
+    ref = torch.nn.functional.layer_norm(zz, (H,), gr, br, 1e-12)
+    ref.backward(dy)
+    assert rel_err(y.float(), ref) < 6e-3 and rel_err(z.float(), zz) < 6e-3
+    for dyk in (dy, dy.bfloat16()):
+        dx, dres, dg, db = K.ln_res_bwd(dyk, z, mean, rstd, gamma, 0.0, 1, 2)
+        assert rel_err(dx.float(), xr.grad) < 2e-2 and torch.equal(dx, dres)
+        assert rel_err(dres.float().view(rows // rr, rr, H).sum(0), rr_.grad) < 2e-2
+        assert rel_err(dg, gr.grad) < 2e-2 and rel_err(db, br.grad) < 2e-2
+    # dropout
+    p = 0.25
+    y2, z2, mean2, rstd2 = K.ln_res_fwd(x, resid, gamma, beta, 1e-12, p, 5, 9)
+    delta = z2.float() - resid.float().repeat(rows // rr, 1)        # = dropout(x) up to the bf16 rounding of z
+    real = x.float().abs() > 0.1                                    # judge only elements whose kept value is clearly != 0
+    dropped = delta.abs() < 0.03
+    assert abs(float(dropped[real].float().mean()) - p) < 0.02
+    assert float((delta[real & ~dropped] / x.float()[real & ~dropped] - 1 / (1 - p)).abs().max()) < 0.08
+    dx2, dres2, _, _ = K.ln_res_bwd(dy, z2, mean2, rstd2, gamma, p, 5, 9)
+    live = real & (dres2.float().abs() > 1e-4)
+    assert bool(((dx2.float() == 0) == dropped)[live].all())
+    y3, _, _, _ = K.ln_res_fwd(x, resid, gamma, beta, 1e-12, p, 5, 10)
+    assert not torch.equal(y2, y3)                                  # another offset, another mask

@@ -77,6 +77,11 @@ SIGNATURES = {
                                  c_size_t, c_void_p]),
     "xtag_symm_ce_bwd": (c_int, [c_void_p, c_int, c_int, ctypes.c_long, c_void_p, c_void_p, c_void_p, c_void_p,
                                  ctypes.c_long, c_void_p]),
+    "xtag_ln_res_bwd_ws_bytes": (c_size_t, [c_int, c_int]),
+    "xtag_ln_res_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int, c_int, c_float, c_float, c_uint64, c_uint64, c_void_p]),
+    "xtag_ln_res_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_int, c_int, c_float, c_uint64, c_uint64, c_void_p, c_size_t, c_void_p]),
     "xtag_asl_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -391,6 +391,50 @@ class CudaKernels:
                                         _stream()), "xtag_symm_ce_bwd")
         return dx
 
+    # ---- K6: dropout + residual + LayerNorm ------------------------------------------------------------
+    def supports_ln_res(self, H: int) -> bool:
+        return H % 256 == 0 and 256 <= H <= 1024
+
+    def ln_res_fwd(self, x: torch.Tensor, resid: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+                   dropout_p: float, seed: int, offset: int):
+        """x [rows, H] bf16, resid [resid_rows, H] (bf16 / fp32, rows % resid_rows == 0) -> (y bf16, z bf16, mean, rstd)"""
+        _cuda(x, resid, gamma, beta)
+        assert x.dtype == torch.bfloat16 and x.dim() == 2 and resid.dim() == 2 and x.shape[1] == resid.shape[1]
+        x, resid = x.contiguous(), resid.contiguous()
+        rows, H = x.shape
+        assert rows % resid.shape[0] == 0
+        dev = x.device
+        z = torch.empty_like(x)
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=dev)
+        rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        check(self.lib.xtag_ln_res_fwd(_p(x), _p(resid), _dt(resid), resid.shape[0], _p(g32), _p(b32), _p(z), _p(y),
+                                       _p(mean), _p(rstd), rows, H, float(eps), float(dropout_p), int(seed), int(offset),
+                                       _stream()), "xtag_ln_res_fwd")
+        return y, z, mean, rstd
+
+    def ln_res_bwd(self, dy: torch.Tensor, z: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
+                   dropout_p: float, seed: int, offset: int):
+        """-> (dx bf16 [rows, H], dresid bf16 [rows, H], dgamma fp32 [H], dbeta fp32 [H])"""
+        _cuda(dy, z, mean, rstd, gamma)
+        rows, H = z.shape
+        dy = dy.reshape(rows, H)
+        if dy.dtype not in _DT:
+            dy = dy.float()
+        dy = dy.contiguous()
+        dev = z.device
+        dx = torch.empty_like(z)
+        dres = torch.empty_like(z)
+        dgb = torch.empty((2, H), dtype=torch.float32, device=dev)
+        g32 = gamma.detach().float().contiguous()
+        nbytes = int(self.lib.xtag_ln_res_bwd_ws_bytes(rows, H))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(self.lib.xtag_ln_res_bwd(_p(dy), _dt(dy), _p(z), _p(mean), _p(rstd), _p(g32), _p(dx), _p(dres),
+                                       dgb[0].data_ptr(), dgb[1].data_ptr(), rows, H, float(dropout_p), int(seed),
+                                       int(offset), _p(ws), nbytes, _stream()), "xtag_ln_res_bwd")
+        return dx, dres, dgb[0], dgb[1]
+
     # ---- K5 ----------------------------------------------------------------------------------
     def asl(self, x: torch.Tensor, y: torch.Tensor, gamma_neg, gamma_pos, clip, eps, want_dx: bool,
             want_idx: bool):

@@ -162,6 +162,35 @@ class _FusedKVProjection(torch.autograd.Function):
         return d_tok, d_w, d_b, None, None, None
 
 
+# ---- K6: dropout + residual + LayerNorm of the dense-output blocks ---------------------------------------------------
+class _ResidualDropoutLayerNorm(torch.autograd.Function):
+    """y = LayerNorm(dropout(x) + resid) (bert.py:281-292, 359-370) as one pass forward and one pass backward
+    (`xtag_ln_res_fwd/bwd`); x [b, L, H] bf16 = the dense layer's output, resid [b, L, H] or [1, L, H]."""
+
+    @staticmethod
+    def forward(ctx, x, resid, gamma, beta, eps, p, seed, offset, kernels):
+        K = _kernels(kernels)
+        H = x.shape[-1]
+        y, z, mean, rstd = K.ln_res_fwd(x.reshape(-1, H), resid.reshape(-1, H), gamma, beta, eps, p, seed, offset)
+        ctx.save_for_backward(z, mean, rstd, gamma)
+        ctx.meta = (K, p, seed, offset, tuple(x.shape), tuple(resid.shape), resid.dtype, gamma.dtype, beta.dtype)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, mean, rstd, gamma = ctx.saved_tensors
+        K, p, seed, offset, xshape, rshape, rdt, gdt, bdt = ctx.meta
+        dx, dres, dg, db = K.ln_res_bwd(dy, z, mean, rstd, gamma, p, seed, offset)
+        if rshape[0] != xshape[0]:                  # broadcast residual (layer 0: the shared label embeddings)
+            dres = dres.view(xshape).sum(dim=0, keepdim=True, dtype=torch.float32)
+        d_res = dres.reshape(rshape).to(rdt) if ctx.needs_input_grad[1] else None
+        return dx.view(xshape), d_res, dg.to(gdt), db.to(bdt), None, None, None, None, None
+
+
+def residual_dropout_layer_norm(x, resid, ln: nn.LayerNorm, p: float, seed: int, offset: int, *, _kernels=None):
+    return _ResidualDropoutLayerNorm.apply(x, resid, ln.weight, ln.bias, ln.eps, p, seed, offset, _kernels)
+
+
 # ---- module tree with the reference's parameter names --------------------------------------------
 class _SelfAttn(nn.Module):          # crossattention.self
     def __init__(self, encoder_width: int):
@@ -216,9 +245,11 @@ class TagHead(nn.Module):
     ``tag_forward``.  Use ``TagHead.from_reference(model)`` / ``load_state_dict(filtered)`` to take over the
     weights of a reference ``CLIP`` and ``patch_reference_model(model)`` to route ``model.tag_forward`` here."""
 
-    def __init__(self, embed_dim: int, tag_list: Optional[List[str]] = None, *, fuse_kv: bool = True, _kernels=None):
+    def __init__(self, embed_dim: int, tag_list: Optional[List[str]] = None, *, fuse_kv: bool = True,
+                 fuse_ln: bool = True, _kernels=None):
         super().__init__()
         self.fuse_kv = fuse_kv
+        self.fuse_ln = fuse_ln
         self.tag_head = _TagBert(embed_dim)
         self.tag_labels = nn.Embedding(TAG_QUERIES, TAG_HIDDEN)
         self.tag_fc = nn.Linear(TAG_HIDDEN, 1)
@@ -273,6 +304,8 @@ class TagHead(nn.Module):
             gbuf = _KVGradBuffer(2 * len(layers) * TAG_HIDDEN)
             fused_kv = (_FusedKVProjection.apply(tag_embeds.to(torch.bfloat16).contiguous(), w, bcat, 2 * len(layers),
                                                  self._k, gbuf), gbuf)
+        K_ = _kernels(self._k)
+        fused_ln = (self.fuse_ln and amp_bf16 and hasattr(K_, "ln_res_fwd") and K_.supports_ln_res(TAG_HIDDEN))
         for li, layer in enumerate(layers):
             ca = layer.crossattention
             if h is None:
@@ -290,11 +323,20 @@ class TagHead(nn.Module):
                 k = ca.self.key(tag_embeds)
                 v = ca.self.value(tag_embeds)
                 ctx = cross_attention(q, k, v, TAG_HEADS, drop, seed, self._step * TAG_LAYERS + li, _kernels=self._k)
-            a = F.dropout(ca.output.dense(ctx.to(k.dtype)), drop, self.training)
-            a = ca.output.LayerNorm(a + resid)
-            f = F.gelu(layer.intermediate.dense(a))
-            o = F.dropout(layer.output.dense(f), drop, self.training)
-            h = layer.output.LayerNorm(o + a)
+            if fused_ln:
+                # dense (library GEMM, bias in its epilogue, bf16 out) -> ONE kernel for dropout + residual + LayerNorm
+                base = ((self._step * TAG_LAYERS + li) << 2) | (1 << 40)      # Philox streams distinct from K4's
+                a = residual_dropout_layer_norm(ca.output.dense(ctx), resid, ca.output.LayerNorm, drop, seed, base,
+                                                _kernels=self._k)
+                f = F.gelu(layer.intermediate.dense(a))
+                h = residual_dropout_layer_norm(layer.output.dense(f), a, layer.output.LayerNorm, drop, seed, base + 1,
+                                                _kernels=self._k)
+            else:
+                a = F.dropout(ca.output.dense(ctx.to(k.dtype)), drop, self.training)
+                a = ca.output.LayerNorm(a + resid)
+                f = F.gelu(layer.intermediate.dense(a))
+                o = F.dropout(layer.output.dense(f), drop, self.training)
+                h = layer.output.LayerNorm(o + a)
         return self.tag_fc(h).squeeze(-1)
 
     forward = tag_forward
@@ -330,6 +372,7 @@ def patch_reference_model(model: nn.Module, *, _kernels=None) -> nn.Module:
     head.tag_list = getattr(model, "tag_list", None)
     head._k, head._step = _kernels, 0
     head.fuse_kv = True
+    head.fuse_ln = True
 
     def tag_forward(tag_embeds):
         head.__dict__["training"] = model.training
