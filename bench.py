@@ -339,6 +339,28 @@ def config_subrecords(dev, world, rank):
             c2.append(rec)
         out["C2_vit_b32_head_sweep_bf16"] = c2
         try:
+            B, D = GLOBAL_BATCH, DIM
+            I, T = _synth(0, B, D, "cpu", torch.bfloat16)
+            I = I.to(dev).requires_grad_(True)
+            T = T.to(dev).requires_grad_(True)
+            ls = torch.tensor(2.3, device=dev, requires_grad=True)
+            lb = torch.tensor(-10.0, device=dev, requires_grad=True)
+            sig = xt.SigLipLoss()
+
+            def step_sig():
+                I.grad = T.grad = ls.grad = lb.grad = None
+                sig(I, T, ls.exp(), lb).backward()
+
+            ms = _time_steps(step_sig, iters=10, warmup=3)
+            out["siglip_C5_shape"] = dict(B=B, D=D, ms_per_step=ms, samples_per_s=B / ms * 1e3,
+                                          algorithmic_tflops=6.0 * B * B * D / (ms * 1e-3) / 1e12,
+                                          what="SigLipLoss fwd+bwd (one pass: loss + staged logit gradient; two gradient "
+                                               "GEMMs): 6*B^2*D executed = algorithmic")
+            del I, T
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out["siglip_C5_shape"] = dict(error=f"{type(e).__name__}: {e}"[:200])
+        try:
             b, N, D = 1024, 197, 512
             head = xt.TagHead(D).to(dev).train()
             asl = xt.AsymmetricLoss(gamma_neg=4, gamma_pos=1, clip=0.05)

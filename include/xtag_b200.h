@@ -293,6 +293,18 @@ int xtag_ln_res_bwd(const void* dy, int dy_dtype, const void* z, const float* me
                     const float* gamma, void* dx, void* dresid, float* dgamma, float* dbeta, int rows, int H,
                     float dropout_p, uint64_t seed, uint64_t offset, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- sigmoid (SigLIP) loss on the contrastive head's mainloop ----------------------------------------------------
+ * (reference src/open_clip/loss.py:314-448;  SURVEY.md section 8f rank 4)
+ *   z_ij = scale * <A_i, Bm_j> + bias;  label_ij = +1 for j == i + label_offset, -1 otherwise (label_offset == -1: all
+ *   -1, the reference's negative_only blocks);  loss = weight * sum_ij softplus(-label_ij * z_ij)
+ * One pass: out3 = { loss, d loss / d scale, d loss / d bias } for a unit upstream gradient, and (stage_ds != 0) the
+ * logit gradient dS staged in ws -- workspace of xtag_clip_bwd_ws_bytes(M, N, D, XTAG_BF16, XTAG_IMPL_TC) bytes, laid
+ * out as xtag_clip_bwd expects it, so the feature gradients are
+ *   xtag_clip_bwd(A, Bm, ..., scale = device scalar (upstream gradient * logit scale), ..., flags = XTAG_BWD_REUSE_DS)
+ * i.e. two GEMMs: 6 M N D executed FLOPs per step in total, no recompute.  bf16, D % 8 == 0. */
+int xtag_siglip_fwd(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale, const float* bias,
+                    int label_offset, float weight, float* out3, void* ws, size_t ws_bytes, int stage_ds, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

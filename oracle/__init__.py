@@ -29,6 +29,7 @@ from .tag_oracle import (  # noqa: F401
     asymmetric_loss,
     control_word_indices,
 )
+from .siglip_oracle import siglip_block_loss, siglip_loss_world  # noqa: F401
 from .fusion_oracle import (  # noqa: F401
     FUSION_CFG,
     make_fusion_params,

@@ -120,6 +120,69 @@ def golden_clip_dist():
     print("clip_dist.npz", len(out))
 
 
+def _siglip_worker(rank, world, port, b, d, scale, bias, seed, impl, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ref = ref_shim.load_ref_loss()
+    I_all, T_all = synth_features(seed, b * world, d, corr=0.4)
+    I = I_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+    T = T_all[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+    sc = torch.tensor(scale, dtype=torch.float64, requires_grad=True)
+    bi = torch.tensor(bias, dtype=torch.float64, requires_grad=True)
+    loss = ref.SigLipLoss(rank=rank, world_size=world, dist_impl=impl)(I, T, sc, bi)
+    loss.backward()
+    key = f"r{rank}_"
+    q.put((rank, {key + "loss": loss.detach().numpy(), key + "dI": I.grad.numpy(), key + "dT": T.grad.numpy(),
+                  key + "dscale": sc.grad.numpy(), key + "dbias": bi.grad.numpy()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def golden_siglip():
+    """The reference's SigLipLoss (loss.py:314-448): single process, and 2 / 3 ranks under gloo with the 'gather'
+    exchange (torch.distributed.nn.all_gather; the other dist_impl variants sum the same terms)."""
+    import torch.multiprocessing as mp
+    ref = ref_shim.load_ref_loss()
+    out = {}
+    for n, (b, d, scale, bias, seed) in enumerate(((12, 16, 10.0, -10.0, 30), (33, 40, 25.0, -4.0, 31),
+                                                   (8, 8, 1.0, 0.5, 32))):
+        I, T = synth_features(seed, b, d, corr=0.4)
+        I.requires_grad_(True)
+        T.requires_grad_(True)
+        sc = torch.tensor(scale, dtype=torch.float64, requires_grad=True)
+        bi = torch.tensor(bias, dtype=torch.float64, requires_grad=True)
+        loss = ref.SigLipLoss()(I, T, sc, bi)
+        loss.backward()
+        pre = f"w1_{n}_"
+        out.update({pre + "I": I.detach().numpy(), pre + "T": T.detach().numpy(), pre + "scale": np.asarray(scale),
+                    pre + "bias": np.asarray(bias), pre + "loss": loss.detach().numpy(), pre + "dI": I.grad.numpy(),
+                    pre + "dT": T.grad.numpy(), pre + "dscale": sc.grad.numpy(), pre + "dbias": bi.grad.numpy()})
+    out["n_w1"] = np.asarray(3)
+    port = 29651
+    for world, b, d, scale, bias, seed in ((2, 6, 16, 10.0, -10.0, 40), (3, 5, 24, 20.0, -3.0, 41)):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_siglip_worker, args=(r, world, port, b, d, scale, bias, seed, "gather", q))
+                 for r in range(world)]
+        for p in procs:
+            p.start()
+        got = [q.get(timeout=300) for _ in range(world)]
+        for p in procs:
+            p.join()
+        port += 1
+        pre = f"w{world}_"
+        I_all, T_all = synth_features(seed, b * world, d, corr=0.4)
+        out.update({pre + "I": I_all.numpy(), pre + "T": T_all.numpy(), pre + "b": np.asarray(b),
+                    pre + "scale": np.asarray(scale), pre + "bias": np.asarray(bias)})
+        for _, res in got:
+            for k, v in res.items():
+                out[pre + k] = v
+    np.savez_compressed(os.path.join(OUT, "siglip.npz"), **out)
+    print("siglip.npz", len(out))
+
+
 def golden_l2norm():
     g = torch.Generator().manual_seed(20)
     x = torch.randn(9, 24, generator=g, dtype=torch.float64)
@@ -272,10 +335,15 @@ def main():
     golden_clip_dist()
     golden_tag_head()
     golden_fusion()
+    golden_siglip()
     golden_config1()
 
 
-if __name__ == "__main__" and "--config1" not in sys.argv:
+if __name__ == "__main__" and "--siglip" in sys.argv:
+    assert ref_shim.available(), "reference tree not found"
+    torch.set_num_threads(4)
+    golden_siglip()
+elif __name__ == "__main__" and "--config1" not in sys.argv:
     main()
 
 

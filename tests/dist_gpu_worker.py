@@ -152,6 +152,23 @@ def main():
     for it in (1, 2):
         if rel(vals[it][0], vals[0][0]) > 1e-6 or rel(vals[it][1], vals[0][1]) > 1e-6:
             failures.append(f"skewed push step {it} rank={rank}: differs from the unskewed step")
+    # sharded SigLipLoss against the oracle's emulation of the reference's per-rank results
+    b, D, scale, bias = 256, 256, 12.0, -8.0
+    g = torch.Generator().manual_seed(77)
+    I_all = torch.nn.functional.normalize(torch.randn(b * world, D, generator=g), dim=-1).bfloat16()
+    T_all = torch.nn.functional.normalize(0.4 * I_all.float() + 0.6 * torch.randn(b * world, D, generator=g), dim=-1).bfloat16()
+    Il = [I_all[r * b:(r + 1) * b].double() for r in range(world)]
+    Tl = [T_all[r * b:(r + 1) * b].double() for r in range(world)]
+    lo, dI, dT, ds, db = oracle.siglip_loss_world(Il, Tl, scale, bias)
+    I = I_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+    T = T_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
+    s = torch.tensor(scale, device=dev, requires_grad=True)
+    bb = torch.tensor(bias, device=dev, requires_grad=True)
+    loss = xt.SigLipLoss(rank=rank, world_size=world)(I, T, s, bb)
+    loss.backward()
+    e = (rel(loss, lo[rank]), rel(I.grad, dI[rank]), rel(T.grad, dT[rank]), rel(s.grad, ds[rank]), rel(bb.grad, db[rank]))
+    if e[0] > 1e-3 or max(e[1:]) > 2e-2:
+        failures.append(f"siglip W={world} rank={rank}: loss {e[0]:.2e} dI {e[1]:.2e} dT {e[2]:.2e} ds {e[3]:.2e} db {e[4]:.2e}")
     n_fail = torch.tensor([len(failures)], device=dev)
     dist.all_reduce(n_fail)
     for f in failures:

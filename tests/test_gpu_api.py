@@ -306,3 +306,64 @@ def test_forward_chunks_gradient_accumulation_gpu(dtype, tol):
     assert rel_err(loss, lo) < (1e-5 if dtype == torch.float32 else 1e-3)
     assert rel_err(ic[live].grad, dI[a:b]) < tol and rel_err(tc[live].grad, dT[a:b]) < tol
     assert abs(float(s.grad) - float(ds)) <= 1e-3 * abs(float(ds)) + 2e-5
+
+
+def test_l2_normalize_into_graph_input_slots():
+    """Features normalised by K3 straight into the captured step's input slots (no input copy at replay): same loss
+    and same gradients w.r.t. the RAW features as normalise -> eager loss."""
+    B, D = 512, 256
+    mod = xt.ClipLoss(cuda_graph=True)
+    g = torch.Generator().manual_seed(4)
+    raw = [(torch.randn(B, D, generator=g), torch.randn(B, D, generator=g)) for _ in range(3)]
+    s = torch.tensor(14.285714, device="cuda")
+    # first call captures the step; from then on the slots exist
+    I0 = xt.l2_normalize(raw[0][0].cuda(), out_dtype=torch.bfloat16).detach().requires_grad_(True)
+    T0 = xt.l2_normalize(raw[0][1].cuda(), out_dtype=torch.bfloat16).detach().requires_grad_(True)
+    mod(I0, T0, s).backward()
+    slots = mod.graph_input_slots(B, D, torch.bfloat16)
+    assert slots is not None
+    for ri, rt in raw[1:]:
+        xi, xt_ = ri.cuda().requires_grad_(True), rt.cuda().requires_grad_(True)
+        I = xt.l2_normalize(xi, out=slots[0])
+        T = xt.l2_normalize(xt_, out=slots[1])
+        assert I.data_ptr() == slots[0].data_ptr() and I.requires_grad
+        loss = mod(I, T, s)
+        loss.backward()
+        yi, yt = ri.cuda().requires_grad_(True), rt.cuda().requires_grad_(True)
+        ref = xt.ClipLoss()(xt.l2_normalize(yi, out_dtype=torch.bfloat16), xt.l2_normalize(yt, out_dtype=torch.bfloat16), s)
+        ref.backward()
+        assert rel_err(loss, ref) < 1e-6 and rel_err(xi.grad, yi.grad) < 1e-5 and rel_err(xt_.grad, yt.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,D,scale,bias", [(256, 512, 10.0, -10.0), (520, 264, 25.0, -4.0), (1024, 1024, 100.0, 0.0),
+                                            (130, 72, 1.0, 0.5)])
+def test_siglip_loss_vs_oracle(B, D, scale, bias):
+    """Fused SigLipLoss (one pass: loss + staged logit gradient; backward = two GEMMs) against the oracle restatement
+    of the reference (loss.py:314-448) on the same bf16 features: loss 1e-3, gradients 2e-2 (max-norm)."""
+    I, T = feats(B + D, B, D, corr=0.4)
+    Ib, Tb = I.bfloat16(), T.bfloat16()
+    Ic, Tc = Ib.cuda().requires_grad_(True), Tb.cuda().requires_grad_(True)
+    s = torch.tensor(scale, device="cuda", requires_grad=True)
+    b = torch.tensor(bias, device="cuda", requires_grad=True)
+    loss = xt.SigLipLoss()(Ic, Tc, s, b)
+    (loss * 1.5).backward()
+    lo, dI, dT, ds, db = oracle.siglip_loss_world([Ib.double()], [Tb.double()], scale, bias)
+    assert rel_err(loss, lo[0]) < 1e-3
+    assert rel_err(Ic.grad, 1.5 * dI[0]) < 2e-2 and rel_err(Tc.grad, 1.5 * dT[0]) < 2e-2
+    assert abs(float(s.grad) - 1.5 * float(ds[0])) <= 2e-2 * abs(1.5 * float(ds[0])) + 1e-4
+    assert abs(float(b.grad) - 1.5 * float(db[0])) <= 2e-2 * abs(1.5 * float(db[0])) + 1e-4
+    with torch.no_grad():                                   # evaluation: no gradient staging
+        assert rel_err(xt.SigLipLoss()(Ic, Tc, s, b), lo[0]) < 1e-3
+
+
+def test_siglip_golden_fp32_inputs_under_autocast(golden_dir):
+    """Reference-generated fixture (tests/golden/siglip.npz) through the drop-in under bf16 autocast."""
+    g = np.load(os.path.join(golden_dir, "siglip.npz"))
+    pre = "w1_1_"
+    D = g[pre + "I"].shape[1]
+    I = torch.from_numpy(g[pre + "I"]).float().cuda()
+    T = torch.from_numpy(g[pre + "T"]).float().cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = xt.SigLipLoss()(I, T, torch.tensor(float(g[pre + "scale"]), device="cuda"),
+                               torch.tensor(float(g[pre + "bias"]), device="cuda"))
+    assert D % 8 == 0 and rel_err(loss, g[pre + "loss"]) < 2e-2

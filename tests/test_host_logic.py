@@ -182,7 +182,10 @@ def test_create_loss_contract():
     m = xt.create_loss(args)
     assert isinstance(m, xt.ClipLoss)
     assert (m.local_loss, m.gather_with_grad, m.cache_labels, m.rank, m.world_size) == (True, True, True, 3, 8)
-    args.siglip = True
+    args.siglip, args.loss_dist_impl = True, "gather"
+    sg = xt.create_loss(args)                      # factory.py:455-461
+    assert isinstance(sg, xt.SigLipLoss) and (sg.rank, sg.world_size, sg.dist_impl) == (3, 8, "gather")
+    args.siglip, args.distill = False, True
     with pytest.raises(NotImplementedError):
         xt.create_loss(args)
 

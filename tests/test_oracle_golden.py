@@ -149,3 +149,28 @@ def test_config1_golden(golden_dir):
     idx = oracle.control_word_indices(logits.detach())
     tl = list(g["tag_list"])
     assert [",".join(tl[i] for i in row) for row in idx.tolist()] == list(g["words"])
+
+
+def test_siglip_oracle_matches_reference(golden_dir):
+    """oracle/siglip_oracle.py against the reference's SigLipLoss (loss.py:314-448): single process and 2 / 3 ranks
+    under gloo with the 'gather' exchange (tests/golden/siglip.npz, oracle/make_golden.py:golden_siglip)."""
+    g = np.load(os.path.join(golden_dir, "siglip.npz"))
+    for n in range(int(g["n_w1"])):
+        pre = f"w1_{n}_"
+        I, T = torch.from_numpy(g[pre + "I"]), torch.from_numpy(g[pre + "T"])
+        lo, dI, dT, ds, db = oracle.siglip_loss_world([I], [T], float(g[pre + "scale"]), float(g[pre + "bias"]))
+        assert abs(float(lo[0]) - float(g[pre + "loss"])) < 1e-10 * max(1.0, abs(float(g[pre + "loss"])))
+        for a, name in ((dI[0], "dI"), (dT[0], "dT"), (ds[0], "dscale"), (db[0], "dbias")):
+            assert np.abs(a.numpy() - g[pre + name]).max() < 1e-10 * max(1.0, np.abs(g[pre + name]).max())
+    for W in (2, 3):
+        pre = f"w{W}_"
+        b = int(g[pre + "b"])
+        I_all, T_all = torch.from_numpy(g[pre + "I"]), torch.from_numpy(g[pre + "T"])
+        Il = [I_all[r * b:(r + 1) * b] for r in range(W)]
+        Tl = [T_all[r * b:(r + 1) * b] for r in range(W)]
+        lo, dI, dT, ds, db = oracle.siglip_loss_world(Il, Tl, float(g[pre + "scale"]), float(g[pre + "bias"]))
+        for r in range(W):
+            k = f"{pre}r{r}_"
+            assert abs(float(lo[r]) - float(g[k + "loss"])) < 1e-10 * max(1.0, abs(float(g[k + "loss"])))
+            for a, name in ((dI[r], "dI"), (dT[r], "dT"), (ds[r], "dscale"), (db[r], "dbias")):
+                assert np.abs(a.numpy() - g[k + name]).max() < 1e-10 * max(1.0, np.abs(g[k + name]).max()), (W, r, name)

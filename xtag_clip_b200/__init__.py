@@ -8,6 +8,7 @@ library or without a CUDA device the ops raise.
     from xtag_clip_b200 import ClipLoss, create_loss, AsymmetricLoss, TagHead, l2_normalize
 """
 from .loss import ClipLoss, gather_features, create_loss                  # noqa: F401
+from .siglip import SigLipLoss                                             # noqa: F401
 from .asymmetric_loss import AsymmetricLoss                               # noqa: F401
 from .tag_head import TagHead, l2_normalize, cross_attention, patch_reference_model   # noqa: F401
 from .fusion_head import FusionHead, DQNCOSLoss, fusion_scores                        # noqa: F401

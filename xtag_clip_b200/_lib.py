@@ -72,6 +72,8 @@ SIGNATURES = {
                                c_float, c_float, c_uint64, c_uint64, c_void_p, c_size_t, c_void_p]),
     "xtag_debug_tile_coords": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "xtag_debug_pick_cluster": (c_int, [c_int, c_int, c_int]),
+    "xtag_siglip_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float,
+                                c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "xtag_symm_ce_ws_bytes": (c_size_t, [c_int]),
     "xtag_symm_ce_fwd": (c_int, [c_void_p, c_int, c_int, ctypes.c_long, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),

@@ -19,6 +19,8 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
                 const float* grad_out, void* dA, void* dB, int grad_dtype, float* dscale,
                 void* ws, size_t ws_bytes, int flags, cudaStream_t st);
 
+int tc_siglip_fwd(const void* A, const void* Bm, int M, int N, int D, const float* scale, const float* bias,
+                  int label_offset, float w, float* out3, void* ws, size_t ws_bytes, int stage_ds, cudaStream_t st);
 void tc_fwd_block_parts(int M, int N, int* row_parts, int* col_parts);
 int tc_clip_fwd_block(const void* A, const void* Bm, int M, int N, int D, const float* scale, int label_offset,
                       float* row_part, float* col_part, int col_ld, float* diag, cudaStream_t st);
@@ -143,4 +145,21 @@ extern "C" int xtag_clip_fwd_stream(const void* A, const void* Bm_all, int dtype
   if (rc) return rc;
   return tc_clip_fwd_stream(A, Bm_all, M, N, D, scale, label_offset, order_host, wait_host, nblk, blk_cols, ready_flags,
                             epoch, row_part, col_part, col_ld, diag, (cudaStream_t)stream);
+}
+
+// ---- sigmoid (SigLIP) loss, sibling of the contrastive head on the same mainloop -----
+extern "C" int xtag_siglip_fwd(const void* A, const void* Bm, int dtype, int M, int N, int D, const float* scale,
+                               const float* bias, int label_offset, float weight, float* out3, void* ws, size_t ws_bytes,
+                               int stage_ds, void* stream) {
+  XTAG_REQUIRE(A && Bm && scale && bias && out3, XTAG_ERR_INVALID, "siglip_fwd: null pointer");
+  XTAG_REQUIRE(M > 0 && N > 0 && D > 0, XTAG_ERR_INVALID, "siglip_fwd: empty problem M=%d N=%d D=%d", M, N, D);
+  XTAG_REQUIRE(label_offset == -1 || (label_offset >= 0 && (long)label_offset + M <= (long)N), XTAG_ERR_INVALID,
+               "siglip_fwd: labels [%d, %d) fall outside the %d columns", label_offset, label_offset + M, N);
+  XTAG_REQUIRE(tc_eligible(dtype, D), XTAG_ERR_UNSUPPORTED,
+               "siglip_fwd: tcgen05 path only (bf16 inputs, D %% 8 == 0)");
+  int rc = xtag_device_check();
+  if (rc) return rc;
+  // label_offset == -1: a column block without positives -- every label is -1 (reference negative_only=True)
+  return tc_siglip_fwd(A, Bm, M, N, D, scale, bias, label_offset < 0 ? -(1 << 30) : label_offset, weight, out3, ws,
+                       ws_bytes, stage_ds, (cudaStream_t)stream);
 }

@@ -52,7 +52,7 @@ struct Geo {
 };
 constexpr int kMaxStages = 6;
 
-enum { EPI_LSE = 0, EPI_DS = 1, EPI_STORE = 2, EPI_BIAS = 3 };
+enum { EPI_LSE = 0, EPI_DS = 1, EPI_STORE = 2, EPI_BIAS = 3, EPI_SIG = 4 };
 
 struct EpiParams {
   // EPI_LSE
@@ -82,6 +82,15 @@ struct EpiParams {
   // its raw fp32 partial to C + ks * split_stride (a workspace), a second kernel sums the slices into the real output
   int split_k;            // 0 / 1: no split
   long split_stride;      // elements between consecutive partial slabs
+  // EPI_SIG (sigmoid loss): z = scale * acc + *bias_p; label +1 on column gi + label_offset, -1 elsewhere;
+  // loss = w_sig * sum softplus(-label * z); dS (for a unit upstream gradient) = -label * w_sig * sigmoid(-label * z),
+  // staged as bf16 like EPI_DS when sig_store != 0.  Partials per epilogue warp: loss_part, dscale_part (sum dS * acc),
+  // dbias_part (sum dS).
+  const float* bias_p;
+  float w_sig;
+  int sig_store;
+  float* loss_part;
+  float* dbias_part;
   // streamed forward (EPI_LSE over a gather buffer that fills up block by block): column block k of blk_tiles n tiles
   // is is one slab of the tile schedule, slabs are visited in arrival order; ready_flags[blk] == *epoch_p once block blk has landed
   const int* ready_flags; // device [nblk] or nullptr
@@ -469,6 +478,65 @@ __device__ __forceinline__ void bias_tile(const EpiParams& ep, const CUtensorMap
   }
 }
 
+// Sigmoid (SigLIP) loss epilogue, reference src/open_clip/loss.py:345-359: ONE pass yields the loss AND the complete
+// logit gradient (no row / column normaliser exists, so nothing has to be known before the pass): the backward is
+// just the two gradient GEMMs on the staged dS -- 6 B^2 D executed FLOPs per step, the algorithmic count.
+// acc3: this thread's partial sums (loss, sum dS * acc, sum dS).
+template <bool FULL>
+__device__ __forceinline__ void sig_tile(const EpiParams& ep, const CUtensorMap* tmC, uint32_t taddr, uint32_t ostage,
+                                         int gi, int row_blk, int n_base, int lane, int M, int N, float (&acc3)[3]) {
+  const float s = ep.scale_p[0], bias = ep.bias_p[0], w = ep.w_sig;
+  const bool row_ok = FULL || gi < M;
+  const int lab = gi + ep.label_offset;
+  float lsum[2] = {0.f, 0.f}, dsa[2] = {0.f, 0.f}, dsb[2] = {0.f, 0.f};
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + ch * 32, r);
+    tmem_ld_wait();
+    const int c0 = n_base + ch * 32;
+    float d[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float a = __uint_as_float(r[j]);
+      const float z = fmaf(a, s, bias);
+      const bool pos = (lab == c0 + j);
+      const float t = pos ? -z : z;                          // -label * z
+      const float e = fast_exp2(-fabsf(t) * kLog2e);         // exp(-|t|) in (0, 1]
+      const float inv = __frcp_rn(1.f + e);
+      const float sp = fmaxf(t, 0.f) + fast_log2(1.f + e) * kLn2;      // softplus(t) = -logsigmoid(label * z)
+      const float sg = (t >= 0.f) ? inv : e * inv;                      // sigmoid(t)
+      const bool ok = row_ok && (FULL || (c0 + j) < N);
+      const float dv = ok ? (pos ? -w * sg : w * sg) : 0.f;             // d loss / d z
+      d[j] = dv;
+      lsum[j & 1] += ok ? sp : 0.f;
+      dsa[j & 1] = fmaf(dv, a, dsa[j & 1]);
+      dsb[j & 1] += dv;
+    }
+    if (ep.sig_store) {
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t p0 = pack2_bf16(d[u * 8 + 0], d[u * 8 + 1]), p1 = pack2_bf16(d[u * 8 + 2], d[u * 8 + 3]);
+        uint32_t p2 = pack2_bf16(d[u * 8 + 4], d[u * 8 + 5]), p3 = pack2_bf16(d[u * 8 + 6], d[u * 8 + 7]);
+        const uint32_t off = (uint32_t)(lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ostage + off), "r"(p0), "r"(p1), "r"(p2), "r"(p3)
+                     : "memory");
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, ostage, c0, row_blk);
+        tma_store_commit();
+      }
+    }
+  }
+  acc3[0] += (lsum[0] + lsum[1]) * w;
+  acc3[1] += dsa[0] + dsa[1];
+  acc3[2] += dsb[0] + dsb[1];
+}
+
 // A_MN / B_MN: the operand is stored "MN-major": global tensor [K rows][M or N contiguous] (e.g. dS read as the
 // A operand of dB = dS^T A, or row-major features read as the B operand [N=D][K] of dA = dS Bm).  TMA then loads
 // 64-element (128 B) wide boxes of BK rows; UMMA reads them through an MN-major 128B-swizzle descriptor.
@@ -751,6 +819,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     float dscale_acc = 0.f;
+    [[maybe_unused]] float sig_acc[3] = {0.f, 0.f, 0.f};
     [[maybe_unused]] const uint64_t store_policy = (ep.tune & kTuneStoreEvictFirst) ? l2_policy_evict_first() : 0;
     for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
       int m_blk, n_blk;
@@ -845,6 +914,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_tempty<CG>(tempty);
+      } else if constexpr (EPI == EPI_SIG) {
+        mbar_wait(tfull, acc_phase);
+        tc_fence_after();
+        const uint32_t ostage = smem_u32(out_stage + e * 2048);
+        if (interior) sig_tile<true>(ep, &tmC, taddr, ostage, gi, m_blk * BM + q * 32, n_base, lane, M, N, sig_acc);
+        else          sig_tile<false>(ep, &tmC, taddr, ostage, gi, m_blk * BM + q * 32, n_base, lane, M, N, sig_acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_tempty<CG>(tempty);
       } else if constexpr (EPI == EPI_BIAS) {
         mbar_wait(tfull, acc_phase);
         tc_fence_after();
@@ -865,6 +943,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if constexpr (EPI == EPI_BIAS) {
       if (lane == 0) tma_store_wait_all();
+    }
+    if constexpr (EPI == EPI_SIG) {
+      if (lane == 0) tma_store_wait_all();
+      const float l0 = warp_sum(sig_acc[0]), l1 = warp_sum(sig_acc[1]), l2 = warp_sum(sig_acc[2]);
+      if (lane == 0) {
+        ep.loss_part[blockIdx.x * kEpiWarps + e] = l0;
+        ep.dscale_part[blockIdx.x * kEpiWarps + e] = l1;
+        ep.dbias_part[blockIdx.x * kEpiWarps + e] = l2;
+      }
     }
     if constexpr (EPI == EPI_DS) {
       if (lane == 0) tma_store_wait_all();               // dS tiles fully written before the kernel ends
@@ -950,7 +1037,7 @@ static int launch_tc_cl(const void* A, long lda, const void* B, long ldb, int M,
   XTAG_CUDA(sync_spin_timeout());
   CUtensorMap tmA, tmB, tmC;
   memset(&tmC, 0, sizeof(tmC));
-  if (EPI == EPI_DS) {
+  if (EPI == EPI_DS || (EPI == EPI_SIG && ep.sig_store)) {
     int rcC = make_store_tmap_bf16(&tmC, ep.dS, M, N, ep.ldds);
     if (rcC) return rcC;
   }
@@ -1188,7 +1275,7 @@ static BwdLayout bwd_layout(int M, int N, int D) {
   L.Np = ((size_t)N + 7) & ~(size_t)7;
   size_t o = 0;
   L.off_ds = o;   o += align256((size_t)M * L.Np * 2);
-  L.off_part = o; o += align256((size_t)256 * kEpiWarps * 4);
+  L.off_part = o; o += align256((size_t)3 * 256 * kEpiWarps * 4);    // per-warp partials (the sigmoid loss has three)
   // split-K slabs of the gradient GEMMs (small problems only: large ones have enough tiles).  Sized for the
   // default tuning so that the workspace size does not depend on a runtime knob.
   const size_t sa = split_ws_bytes(M, D, (int)L.Np, 0), sb = split_ws_bytes(N, D, M, 0);
@@ -1243,6 +1330,37 @@ int tc_clip_bwd(const void* A, const void* Bm, int M, int N, int D, const float*
     // B operand (n=d, k=i) is A read as [K=i rows][N=d contiguous]: both MN-major, nothing is transposed
     es.C = dB;
     rc = gemm_store<true, true>(dS, (long)L.Np, A, (long)D, N, D, M, es, w + L.off_split, L.split_bytes, st);
+    if (rc) return rc;
+  }
+  return XTAG_OK;
+}
+
+// Sigmoid loss forward: loss, d loss / d logit_scale and d loss / d logit_bias for a unit upstream gradient in out3, and
+// (stage_ds) the logit gradient dS staged in ws exactly where tc_clip_bwd(XTAG_BWD_REUSE_DS) expects it.
+int tc_siglip_fwd(const void* A, const void* Bm, int M, int N, int D, const float* scale, const float* bias,
+                  int label_offset, float w, float* out3, void* ws, size_t ws_bytes, int stage_ds, cudaStream_t st) {
+  const BwdLayout L = bwd_layout(M, N, D);
+  XTAG_REQUIRE(ws && ws_bytes >= L.total, XTAG_ERR_WORKSPACE, "siglip_fwd: workspace %zu < %zu", ws_bytes, L.total);
+  uint8_t* wsb = (uint8_t*)ws;
+  __nv_bfloat16* dS = (__nv_bfloat16*)(wsb + L.off_ds);
+  float* part = (float*)(wsb + L.off_part);
+  if (stage_ds && L.Np != (size_t)N) XTAG_CUDA(cudaMemsetAsync(dS, 0, (size_t)M * L.Np * 2, st));
+  XTAG_CUDA(cudaMemsetAsync(out3, 0, 3 * sizeof(float), st));
+  EpiParams ep = {};
+  ep.scale_p = scale;
+  ep.bias_p = bias;
+  ep.label_offset = label_offset;
+  ep.w_sig = w;
+  ep.sig_store = stage_ds ? 1 : 0;
+  ep.dS = dS; ep.ldds = (int)L.Np;
+  ep.loss_part = part;
+  ep.dscale_part = part + 256 * kEpiWarps;
+  ep.dbias_part = part + 2 * 256 * kEpiWarps;
+  int grid = 0;
+  int rc = launch_tc<EPI_SIG, false, false>(A, D, Bm, D, M, N, D, ep, st, &grid);
+  if (rc) return rc;
+  for (int k = 0; k < 3; ++k) {
+    rc = launch_sum_into(part + k * 256 * kEpiWarps, grid * kEpiWarps, out3 + k, st);
     if (rc) return rc;
   }
   return XTAG_OK;

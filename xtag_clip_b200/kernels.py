@@ -49,11 +49,18 @@ class CudaKernels:
         self.impl = impl
 
     # ---- K3 ----------------------------------------------------------------------------------
-    def l2norm_fwd(self, x: torch.Tensor, out_dtype: torch.dtype, eps: float, want_transposed: bool = False):
-        _cuda(x)
+    def l2norm_fwd(self, x: torch.Tensor, out_dtype: torch.dtype, eps: float, want_transposed: bool = False,
+                   out: Optional[torch.Tensor] = None):
+        """out: write the normalised rows into this contiguous [rows, dim] tensor (e.g. an input slot of the loss)."""
+        _cuda(x, out)
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         rows, dim = x2.shape
-        y = torch.empty((rows, dim), dtype=out_dtype, device=x.device)
+        if out is not None:
+            assert out.is_contiguous() and out.numel() == rows * dim, "out must be a contiguous [rows, dim] tensor"
+            out_dtype = out.dtype
+            y = out.view(rows, dim)
+        else:
+            y = torch.empty((rows, dim), dtype=out_dtype, device=x.device)
         yT = torch.empty((dim, rows), dtype=out_dtype, device=x.device) if want_transposed else None
         inv = torch.empty((rows,), dtype=torch.float32, device=x.device)
         if rows:
@@ -273,6 +280,26 @@ class CudaKernels:
         if return_ws:
             return dA, dB, dscale, ws
         return dA, dB, dscale
+
+    # ---- sigmoid (SigLIP) loss on the same mainloop ------------------------------------------------------
+    def siglip_fwd(self, A: torch.Tensor, Bm: torch.Tensor, scale: torch.Tensor, bias: torch.Tensor, label_offset: int,
+                   weight: float, stage_ds: bool = True):
+        """-> (out3 fp32 [3] = loss, d loss/d scale, d loss/d bias for a unit upstream gradient; ws | None).  ws holds
+        the staged logit gradient for `clip_bwd(..., ws=ws, reuse_ds=True)`."""
+        _cuda(A, Bm, scale, bias)
+        assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16 and A.shape[1] == Bm.shape[1]
+        A, Bm = A.contiguous(), Bm.contiguous()
+        M, D = A.shape
+        N = Bm.shape[0]
+        nbytes = int(self.lib.xtag_clip_bwd_ws_bytes(M, N, D, XTAG_BF16, _lib.IMPL_TC))
+        if nbytes == 0:
+            check(-1, "xtag_clip_bwd_ws_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+        out3 = torch.empty(3, dtype=torch.float32, device=A.device)
+        check(self.lib.xtag_siglip_fwd(_p(A), _p(Bm), XTAG_BF16, M, N, D, _p(scale), _p(bias), int(label_offset),
+                                       float(weight), _p(out3), _p(ws), nbytes, int(bool(stage_ds)), _stream()),
+              "xtag_siglip_fwd")
+        return out3, (ws if stage_ds else None)
 
     def tc_gemm_nt(self, A: torch.Tensor, B: torch.Tensor, out_dtype=torch.float32, alpha: float = 1.0):
         _cuda(A, B)

@@ -770,13 +770,16 @@ class ClipLoss(nn.Module):
 
 
 def create_loss(args):
-    """Reference factory contract (factory.py:433-469) for the losses in scope: returns the fused
-    ``ClipLoss`` configured from ``args.local_loss / gather_with_grad / rank / world_size / horovod``.
-    Distill / CoCa / SigLIP losses are outside the hot path (SURVEY.md section 2, #2)."""
-    if getattr(args, "distill", False) or getattr(args, "siglip", False) or \
-            "coca" in str(getattr(args, "model", "")).lower():
-        raise NotImplementedError("xtag_clip_b200.create_loss covers the ClipLoss path only "
-                                  "(--distill / --siglip / coca models are out of scope)")
+    """Reference factory contract (factory.py:433-469) for the losses in scope: the fused ``ClipLoss`` configured from
+    ``args.local_loss / gather_with_grad / rank / world_size / horovod``, or the fused ``SigLipLoss`` for
+    ``args.siglip``.  Distill / CoCa losses are outside the hot path (SURVEY.md section 2, #2)."""
+    if getattr(args, "distill", False) or "coca" in str(getattr(args, "model", "")).lower():
+        raise NotImplementedError("xtag_clip_b200.create_loss covers the ClipLoss / SigLipLoss paths only "
+                                  "(--distill and coca models are out of scope)")
+    if getattr(args, "siglip", False):
+        assert not args.horovod, "Horovod not currently supported for SigLip"
+        from .siglip import SigLipLoss
+        return SigLipLoss(rank=args.rank, world_size=args.world_size, dist_impl=getattr(args, "loss_dist_impl", None))
     return ClipLoss(
         local_loss=args.local_loss,
         gather_with_grad=args.gather_with_grad,

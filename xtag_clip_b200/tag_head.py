@@ -44,9 +44,14 @@ def _kernels(k=None):
 # ---- K3 -------------------------------------------------------------------------------------------
 class _L2Normalize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, eps, out_dtype, kernels):
+    def forward(ctx, x, eps, out_dtype, kernels, out):
         K = _kernels(kernels)
-        y, inv, _ = K.l2norm_fwd(x, out_dtype or x.dtype, eps)
+        if out is not None:
+            y, inv, _ = K.l2norm_fwd(x, out.dtype, eps, out=out)
+            ctx.mark_dirty(out)
+            y = out
+        else:
+            y, inv, _ = K.l2norm_fwd(x, out_dtype or x.dtype, eps)
         ctx.save_for_backward(y, inv)
         ctx.meta = (K, eps, x.dtype)
         return y
@@ -55,12 +60,18 @@ class _L2Normalize(torch.autograd.Function):
     def backward(ctx, gy):
         y, inv = ctx.saved_tensors
         K, eps, in_dtype = ctx.meta
-        return K.l2norm_bwd(gy, y, inv, in_dtype, eps), None, None, None
+        return K.l2norm_bwd(gy, y, inv, in_dtype, eps), None, None, None, None
 
 
-def l2_normalize(x: torch.Tensor, eps: float = 1e-12, out_dtype: Optional[torch.dtype] = None, *, _kernels=None):
-    """``F.normalize(x, dim=-1)`` (model.py:313, 333) with an optional fused cast of the output."""
-    return _L2Normalize.apply(x, eps, out_dtype, _kernels)
+def l2_normalize(x: torch.Tensor, eps: float = 1e-12, out_dtype: Optional[torch.dtype] = None, *,
+                 out: Optional[torch.Tensor] = None, _kernels=None):
+    """``F.normalize(x, dim=-1)`` (model.py:313, 333) with an optional fused cast of the output.
+    ``out``: write the result straight into this [rows, dim] tensor -- an input slot of the contrastive loss
+    (``ClipLoss.graph_input_slots``: for a sharded, captured step the text slot IS the rank's block of the
+    symmetric-memory gather buffer), so the features are written once, already in bf16, where K1 and the peers read
+    them.  The returned tensor is ``out`` with autograd history."""
+    # (a fresh alias of the slot: the in-place output must not inherit the autograd history of the previous step)
+    return _L2Normalize.apply(x, eps, out_dtype, _kernels, out.detach() if out is not None else None)
 
 
 # ---- K4 -------------------------------------------------------------------------------------------
