@@ -229,27 +229,39 @@ class ClockSampler:
 
 def _bind_to_gpu_numa_node(local_rank: int):
     """Pin this process to the CPUs of the GPU's NUMA node BEFORE any pinned host memory is allocated: with 8 ranks
-    on one host the per-step H2D copies otherwise cross the socket interconnect.  Best effort."""
+    on one host the per-step H2D copies otherwise cross the socket interconnect (measured: 23 GB/s per GPU with all 8
+    copying at once).  Best effort; returns what it did for the JSON line."""
     try:
-        import torch
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
-        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
-        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
-        bdf = f"{dom:04x}:{bus:02x}:{dev:02x}.0"
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].strip().isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        bdf = f"{int(dom, 16):04x}:{rest.lower()}"
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
         if node < 0:
-            return None
+            return dict(numa_node=node, bound=False)
         cpus = []
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
             cpus.extend(range(int(lo), int(hi or lo) + 1))
         allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-            return dict(numa_node=node, cpus=len(allowed))
-    except Exception:
-        return None
-    return None
+        if not allowed:
+            return dict(numa_node=node, bound=False)
+        os.sched_setaffinity(0, allowed)
+        try:                                   # prefer memory of that node for the pinned buffers allocated next
+            import ctypes as _ct
+            libnuma = _ct.CDLL("libnuma.so.1")
+            if libnuma.numa_available() >= 0:
+                libnuma.numa_set_preferred(node)
+        except Exception:
+            pass
+        return dict(numa_node=node, cpus=len(allowed), bound=True)
+    except Exception as e:
+        return dict(bound=False, why=f"{type(e).__name__}: {e}"[:120])
 
 
 def _ncu_traffic(kernel_sig: str):

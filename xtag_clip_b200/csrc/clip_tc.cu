@@ -80,6 +80,7 @@ struct EpiParams {
   const float* bias;      // [N] fp32 or nullptr
   // EPI_STORE split-K: the K loop is cut into split_k slices, scheduled as split_k x tiles work items; slice ks writes
   // its raw fp32 partial to C + ks * split_stride (a workspace), a second kernel sums the slices into the real output
+  int group_m;            // m tiles per group of the tile schedule (0: default kGroupM / CG)
   int split_k;            // 0 / 1: no split
   long split_stride;      // elements between consecutive partial slabs
   // EPI_SIG (sigmoid loss): z = scale * acc + *bias_p; label +1 on column gi + label_offset, -1 elsewhere;
@@ -582,7 +583,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int S = (EPI == EPI_STORE && ep.split_k > 1) ? ep.split_k : 1;
   const int kb_per = (num_k_all + S - 1) / S;
   const int num_tiles = num_m * num_n * S;
-  constexpr int kGroup = kGroupM / CG;            // same operand footprint per wave in both modes
+  // m tiles per schedule group: kGroupM / CG by default (same operand footprint per wave in both modes); 1 = the n
+  // tiles of one m tile are consecutive (outputs with few n tiles: all CTAs that share an A row block run together)
+  const int kGroup = ep.group_m > 0 ? ep.group_m : kGroupM / CG;
   const int tile_first = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int slab_req = (ep.tune >> 16) & 0xff;                    // n tiles per slab of the tile schedule (0: one slab)
@@ -1109,6 +1112,14 @@ static int launch_tc(const void* A, long lda, const void* B, long ldb, int M, in
                      cudaStream_t st, int* grid_used = nullptr) {
   EpiParams ep = ep_in;
   ep.tune = tc_tune();
+  // Plain GEMMs with few n tiles (dA / dB of the contrastive head: N = D = 1024 -> 4 n tiles, K = 32768): visit the n
+  // tiles of one m tile back to back.  With the default groups of 8 m x 4 n = 32 tiles a wave of 74 CTA pairs cuts
+  // through a group, and the tiles on the far side re-read their A row blocks -- the 2 GiB dS -- from HBM one K loop
+  // later (ncu: 4.4 GB read per launch against 2.2 GB algorithmic).
+  // (not with the multicast clusters of the single-CTA kernels, whose CTAs take consecutive m tiles of one n tile)
+  if (EPI == EPI_STORE && (N + BN - 1) / BN <= 8 && ep.group_m == 0 &&
+      (pick_pair(M, ep.tune) || pick_cluster(M, N, ep.tune) == 1))
+    ep.group_m = 1;
   const int num_n = (N + BN - 1) / BN * ((EPI == EPI_STORE && ep.split_k > 1) ? ep.split_k : 1);   // x K slices
   if (pick_pair(M, ep.tune)) {
     const int num_pairs = ((M + 2 * BM - 1) / (2 * BM)) * num_n;
