@@ -439,13 +439,23 @@ __global__ void __launch_bounds__(256) lse_combine_loss_kernel(const float* cons
     last = atomicAdd(scratch, 1ull) == (unsigned long long)(gridDim.x - 1);
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last) {
+    // the whole block sums the partials: a fixed tree (deterministic), not one thread walking gridDim.x values
     __threadfence();
     double t = 0.0;
-    for (unsigned k = 0; k < gridDim.x; ++k) t += reinterpret_cast<volatile double*>(partials)[k];
-    loss_out[0] = (float)(0.5 * t / (double)M);
-    if (epoch) epoch[0] += 1;
-    scratch[0] = 0ull;                      // ready for the next launch
+    for (unsigned k = threadIdx.x; k < gridDim.x; k += blockDim.x) t += reinterpret_cast<volatile double*>(partials)[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();                        // red[] was read by thread 0 above
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int k = 0; k < 8; ++k) tot += red[k];
+      loss_out[0] = (float)(0.5 * tot / (double)M);
+      if (epoch) epoch[0] += 1;
+      scratch[0] = 0ull;                    // ready for the next launch
+    }
   }
 }
 
