@@ -367,3 +367,60 @@ def test_siglip_golden_fp32_inputs_under_autocast(golden_dir):
         loss = xt.SigLipLoss()(I, T, torch.tensor(float(g[pre + "scale"]), device="cuda"),
                                torch.tensor(float(g[pre + "bias"]), device="cuda"))
     assert D % 8 == 0 and rel_err(loss, g[pre + "loss"]) < 2e-2
+
+
+def test_cliploss_autocast_fp32_features_take_the_bf16_path():
+    """The reference's amp_bf16 loop calls the loss inside torch.autocast on fp32 features (F.normalize is promoted to
+    fp32); its own matmul then runs in bf16.  The drop-in must do the same: tcgen05 path, identical numbers to passing
+    bf16-cast features, gradients returned in fp32; outside autocast fp32 features keep the exact fp32 path."""
+    from xtag_clip_b200 import _lib
+    I, T = feats(21, 512, 256)
+    Ic, Tc = I.cuda().requires_grad_(True), T.cuda().requires_grad_(True)
+    s = torch.tensor(14.285714, device="cuda", requires_grad=True)
+    lib = _lib.load()
+    lib.xtag_prof_enable(1)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = xt.ClipLoss()(Ic, Tc, s)
+    loss.backward()
+    torch.cuda.synchronize()
+    import ctypes
+    tags, tms, work = (ctypes.c_int * 64)(), (ctypes.c_float * 64)(), (ctypes.c_double * 64)()
+    n = lib.xtag_prof_read(tags, tms, work, 64)
+    lib.xtag_prof_enable(0)
+    assert n >= 4 and {tags[i] for i in range(n)} == {0, 1, 2}          # the tcgen05 kernels ran (fwd, dS, 2 GEMMs)
+    Ib, Tb = I.bfloat16().cuda().requires_grad_(True), T.bfloat16().cuda().requires_grad_(True)
+    s2 = torch.tensor(14.285714, device="cuda", requires_grad=True)
+    ref = xt.ClipLoss()(Ib, Tb, s2)
+    ref.backward()
+    assert Ic.grad.dtype == torch.float32 and float(loss) == float(ref)
+    assert torch.equal(Ic.grad, Ib.grad.float()) and torch.equal(Tc.grad, Tb.grad.float())
+    exact = xt.ClipLoss()(I.cuda(), T.cuda(), 14.285714)                   # no autocast: exact fp32 mode
+    lo = oracle.clip_loss_single(I.double(), T.double(), torch.tensor(14.285714, dtype=torch.float64))
+    assert rel_err(exact, lo) < 1e-5
+    forced = xt.ClipLoss(compute_dtype=torch.bfloat16)(I.cuda(), T.cuda(), 14.285714)
+    assert float(forced) == float(ref)
+    with pytest.raises(ValueError):
+        xt.ClipLoss(compute_dtype=torch.float16)
+    assert rel_err(xt.ClipLoss()(I.double().cuda(), T.double().cuda(), 14.285714), lo) < 1e-5    # fp64 in -> fp32 mode
+
+
+def test_cliploss_cuda_graph_second_forward_before_backward():
+    """A captured step has ONE set of saved activations: a second forward of the same signature before the first one's
+    backward must not overwrite them (it runs eagerly); both backwards give the right gradients."""
+    mod, eager = xt.ClipLoss(cuda_graph=True), xt.ClipLoss()
+    pairs = []
+    for seed in (31, 32):
+        I, T = feats(seed, 384, 256, corr=0.2)
+        pairs.append((I.bfloat16().cuda(), T.bfloat16().cuda()))
+    warm = [t.clone().requires_grad_(True) for t in pairs[0]]
+    mod(warm[0], warm[1], 10.0).backward()                                  # capture
+    xs = [[t.clone().requires_grad_(True) for t in p] for p in pairs]
+    l0 = mod(xs[0][0], xs[0][1], 10.0)
+    l1 = mod(xs[1][0], xs[1][1], 10.0)                                      # first backward still outstanding
+    l1.backward()
+    l0.backward()
+    for (a, b), p in zip(xs, pairs):
+        ra, rb = p[0].clone().requires_grad_(True), p[1].clone().requires_grad_(True)
+        eager(ra, rb, 10.0).backward()
+        assert rel_err(a.grad, ra.grad) < 1e-5 and rel_err(b.grad, rb.grad) < 1e-5
+    assert rel_err(l0, eager(pairs[0][0], pairs[0][1], 10.0)) < 1e-6
