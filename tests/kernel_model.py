@@ -118,6 +118,12 @@ class ModelKernels:
         s = float(scale.reshape(-1)[0])
         g = float(grad_out.reshape(-1)[0])
         A64, B64 = _f64(A), _f64(Bm)
+        if reuse_ds and torch.is_tensor(ws):
+            # XTAG_BWD_REUSE_DS on a logit gradient staged by another producer (siglip_fwd): two GEMMs, alpha = scale
+            dS = _f64(ws)
+            dA = (s * dS @ B64).to(grad_dtype) if need_dA else None
+            dB = (s * dS.T @ A64).to(grad_dtype) if need_dB else None
+            return dA, dB, torch.zeros((), dtype=torch.float32)
         raw = A64 @ B64.T
         S = s * raw
         M, N = S.shape
@@ -136,6 +142,23 @@ class ModelKernels:
         if return_ws:
             return dA, dB, ds, "ws"
         return dA, dB, ds
+
+    # sigmoid loss on the contrastive mainloop (xtag_siglip_fwd): out3 = (loss, dloss/dscale, dloss/dbias) for a unit
+    # upstream gradient; "ws" = the staged logit gradient
+    def siglip_fwd(self, A, Bm, scale, bias, label_offset, weight, stage_ds=True):
+        self.calls.append(("siglip_fwd", tuple(A.shape), tuple(Bm.shape), int(label_offset)))
+        s, b0 = float(scale.reshape(-1)[0]), float(bias.reshape(-1)[0])
+        raw = _f64(A) @ _f64(Bm).T
+        z = s * raw + b0
+        M, N = z.shape
+        lab = -torch.ones(M, N, dtype=torch.float64)
+        if label_offset >= 0:
+            lab[torch.arange(M), torch.arange(M) + label_offset] = 1.0
+        t = -lab * z
+        loss = weight * torch.nn.functional.softplus(t).sum()
+        dS = -lab * weight * torch.sigmoid(t)
+        out3 = torch.stack([loss, (dS * raw).sum(), dS.sum()]).float()
+        return out3, (dS if stage_ds else None)
 
     # K4
     @staticmethod

@@ -336,3 +336,59 @@ def test_streamed_forward_and_symmetric_backward_host_logic(world, port):
         assert push["log"] == ["gather_pushed", ("end_gather", True), "reduce_scatter_begin", "push_step_done"]
     for p in procs:
         p.join(timeout=60)
+
+
+def _worker_siglip(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import xtag_clip_b200 as xt
+    from kernel_model import ModelKernels
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "siglip.npz"))
+        pre = f"w{world}_"
+        b = int(g[pre + "b"])
+        I = torch.from_numpy(g[pre + "I"])[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+        T = torch.from_numpy(g[pre + "T"])[rank * b:(rank + 1) * b].clone().requires_grad_(True)
+        s = torch.tensor(float(g[pre + "scale"]), dtype=torch.float64, requires_grad=True)
+        bi = torch.tensor(float(g[pre + "bias"]), dtype=torch.float64, requires_grad=True)
+        k = ModelKernels()
+        loss = xt.SigLipLoss(rank=rank, world_size=world, dist_impl="gather", compute_dtype=torch.bfloat16,
+                             _kernels=k)(I, T, s, bi)
+        loss.backward()
+        key = f"{pre}r{rank}_"
+        # the drop-in rounds the features to bf16 (its compute dtype); the fixture is the reference's fp64 run
+        res = dict(e_loss=rel_err(loss.item(), float(g[key + "loss"])), e_di=rel_err(I.grad.numpy(), g[key + "dI"]),
+                   e_dt=rel_err(T.grad.numpy(), g[key + "dT"]),
+                   e_ds=abs(float(s.grad) - float(g[key + "dscale"])) / max(abs(float(g[key + "dscale"])), 1e-12),
+                   e_db=abs(float(bi.grad) - float(g[key + "dbias"])) / max(abs(float(g[key + "dbias"])), 1e-12),
+                   calls=list(k.calls))
+        q.put((rank, res, None))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,port", [(2, 29741), (3, 29742)])
+def test_siglip_sharded_host_logic_vs_reference_fixture(world, port):
+    """Sharded SigLipLoss under gloo with the CPU contract model: every rank's loss and gradients against what the
+    REFERENCE's SigLipLoss(dist_impl='gather') produced under gloo (tests/golden/siglip.npz) -- own block with
+    positives at label offset rank*b, text gradients reduce-scattered, per-rank scale / bias gradients."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_siglip, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for _ in range(world):
+        rank, res, err = q.get(timeout=300)
+        assert err is None, err
+        assert res["e_loss"] < 2e-2 and res["e_di"] < 3e-2 and res["e_dt"] < 3e-2 and res["e_ds"] < 3e-2 and res["e_db"] < 3e-2, res
+        fwd = [c for c in res["calls"] if c[0] == "siglip_fwd"]
+        assert len(fwd) == 1 and fwd[0][3] == rank * fwd[0][1][0] and fwd[0][2][0] == world * fwd[0][1][0]
+    for p in procs:
+        p.join(timeout=60)
