@@ -581,3 +581,38 @@ def test_ln_res_fused(K, rows, H, rr, rdt):
     assert bool(((dx2.float() == 0) == dropped)[live].all())
     y3, _, _, _ = K.ln_res_fwd(x, resid, gamma, beta, 1e-12, p, 5, 10)
     assert not torch.equal(y2, y3)                                  # another offset, another mask
+
+
+@pytest.mark.parametrize("b,Lq,Lk,H,heads,p", [(3, 200, 77, 512, 4, 0.0), (2, 65, 130, 768, 4, 0.0), (2, 256, 64, 256, 4, 0.0),
+                                               (2, 130, 50, 512, 4, 0.2)])
+def test_xattn_long_query_sets_one_launch(K, MK, b, Lq, Lk, H, heads, p):
+    """Query sets of more than 64 rows (the TQN fusion head: Lq = B queries per sample) in ONE forward launch and a
+    two-launch backward (chunked dQ + looping dK / dV kernel) against the contract model; with dropout: determinism,
+    and the gradient of sum(ctx * w) through the SAME mask equals a finite statement of it (linearity in v)."""
+    g = torch.Generator().manual_seed(Lq + Lk)
+    q = (torch.randn(b, Lq, H, generator=g) * 0.5).bfloat16().cuda()
+    k = (torch.randn(b, Lk, H, generator=g) * 0.5).bfloat16().cuda()
+    v = torch.randn(b, Lk, H, generator=g).bfloat16().cuda()
+    do = torch.randn(b, Lq, H, generator=g).bfloat16().cuda()
+    sc = 1 / math.sqrt(H // heads)
+    o, lse = K.xattn_fwd(q, k, v, heads, sc, p, 11, 5)
+    dq, dk, dv = K.xattn_bwd(q, k, v, o, do, lse, heads, sc, p, 11, 5)
+    assert all(torch.isfinite(t.float()).all() for t in (o, lse, dq, dk, dv))
+    if p == 0.0:
+        om, lm = MK.xattn_fwd(q.cpu(), k.cpu(), v.cpu(), heads, sc, 0.0, 0, 0)
+        dqm, dkm, dvm = MK.xattn_bwd(q.cpu(), k.cpu(), v.cpu(), om, do.cpu(), lm, heads, sc, 0.0, 0, 0)
+        assert rel_err(o.float(), om.float()) < 2e-2 and rel_err(lse, lm) < 1e-3
+        assert rel_err(dq.float(), dqm.float()) < 3e-2 and rel_err(dk.float(), dkm.float()) < 3e-2
+        assert rel_err(dv.float(), dvm.float()) < 3e-2
+        # the 64-row chunks are independent: the first 64 queries alone give the same rows
+        o64, lse64 = K.xattn_fwd(q[:, :64].contiguous(), k, v, heads, sc, 0.0, 0, 0)
+        assert torch.equal(o64, o[:, :64]) and torch.equal(lse64, lse[:, :, :64])
+    else:
+        o2, lse2 = K.xattn_fwd(q, k, v, heads, sc, p, 11, 5)
+        assert torch.equal(o, o2)
+        # ctx is linear in v for a fixed mask: <dO, ctx(v + e)> - <dO, ctx(v)> == <dv, e>
+        e = (torch.randn(b, Lk, H, generator=g) * 0.25).bfloat16().cuda()
+        o3, _ = K.xattn_fwd(q, k, (v.float() + e.float()).bfloat16(), heads, sc, p, 11, 5)
+        lhs = ((o3.float() - o.float()) * do.float()).sum()
+        rhs = (dv.float() * e.float()).sum()
+        assert abs(float(lhs) - float(rhs)) < 5e-2 * max(abs(float(rhs)), 1.0)

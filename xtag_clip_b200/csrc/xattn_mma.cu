@@ -101,7 +101,8 @@ xattn_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
-  const int dh = NCH * 64;
+  const int q0 = blockIdx.y * QROWS;                        // first query row of this CTA (query sets > 64 rows: one
+  const int dh = NCH * 64;                                  // CTA per 64-row chunk, ONE launch for all of them)
   const int num_tiles = (Lk + XA_KT - 1) / XA_KT;
 
   if (tid == 0) {
@@ -128,7 +129,7 @@ xattn_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t qb = smem_u32(&bars[0]);
     mbar_arrive_expect_tx(qb, q_bytes);
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) tma_load_3d(smem_u32(Qs) + c * QROWS * 128, &tmQ, qb, h * dh + c * 64, 0, b);
+    for (int c = 0; c < NCH; ++c) tma_load_3d(smem_u32(Qs) + c * QROWS * 128, &tmQ, qb, h * dh + c * 64, q0, b);
     issue_tile(0);
   }
 
@@ -214,7 +215,7 @@ xattn_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // dropout acts on the normalised probabilities; the normaliser is linear, so masking the unnormalised
       // numerators (after the row sum above) is equivalent
       uint32_t keep[2];
-      dropout_bits_tile(keep, seed, offset, (uint64_t)bh * Lq + row0, key0, (Lk + 3) >> 2, drop_thr, t4);
+      dropout_bits_tile(keep, seed, offset, (uint64_t)bh * Lq + q0 + row0, key0, (Lk + 3) >> 2, drop_thr, t4);
 #pragma unroll
       for (int i = 0; i < XA_KT / 8; ++i) {
 #pragma unroll
@@ -258,7 +259,7 @@ xattn_fwd_mma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int HD = heads * dh;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    const int row = row0 + r * 8;
+    const int row = q0 + row0 + r * 8;
     if (row >= Lq) continue;
     const float inv = 1.f / l_run[r];
     __nv_bfloat16* orow = o + ((size_t)b * Lq + row) * HD + h * dh;
@@ -302,18 +303,21 @@ static int xa_make_tmap(CUtensorMap* tm, const void* base, int b, int L, int col
   return XTAG_OK;
 }
 
-bool xattn_mma_supported(int Lq, int dh) { return (dh == 64 || dh == 128 || dh == 192 || dh == 256) && Lq <= 16 * XA_MAXW; }
+bool xattn_mma_supported(int Lq, int dh) { return (dh == 64 || dh == 128 || dh == 192 || dh == 256) && Lq >= 1; }
+// warps per CTA / query rows per CTA for a query set of Lq rows (more than 64 rows: chunks of 64 on blockIdx.y)
+static int xa_nw(int Lq) { const int nw = (Lq + 15) / 16; return nw > XA_MAXW ? XA_MAXW : nw; }
 
 template <int NCH>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, void* o, float* lse, int b,
                       int Lq, int Lk, int heads, float sl2, float p, uint64_t seed, uint64_t offset, cudaStream_t st) {
-  const int nw = (Lq + 15) / 16;
+  const int nw = xa_nw(Lq);
   const size_t q_bytes = ((size_t)NCH * 16 * nw * 128 + 1023) & ~(size_t)1023;
   const size_t smem = 1024 + q_bytes + 2 * (2 * NCH * XA_KT * 128) + 64;
   XTAG_CUDA(sync_spin_timeout());
   XTAG_CUDA(cudaFuncSetAttribute(xattn_fwd_mma_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  xattn_fwd_mma_kernel<NCH><<<b * heads, 32 * nw, smem, st>>>(tq, tk, tv, (__nv_bfloat16*)o, lse, Lq, Lk, heads, sl2, p,
-                                                              seed, offset);
+  const dim3 grid((unsigned)(b * heads), (unsigned)((Lq + 16 * nw - 1) / (16 * nw)));
+  xattn_fwd_mma_kernel<NCH><<<grid, 32 * nw, smem, st>>>(tq, tk, tv, (__nv_bfloat16*)o, lse, Lq, Lk, heads, sl2, p, seed,
+                                                         offset);
   XTAG_CHECK_LAUNCH();
   return XTAG_OK;
 }
@@ -322,7 +326,7 @@ int xattn_mma_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   int dh, int ldq, int ldk, int ldv, float sm_scale, float p_drop, uint64_t seed, uint64_t offset,
                   cudaStream_t st) {
   CUtensorMap tq, tk, tv;
-  const int nw = (Lq + 15) / 16;
+  const int nw = xa_nw(Lq);
   int rc = xa_make_tmap(&tq, q, b, Lq, heads * dh, ldq, 16 * nw);
   if (rc) return rc;
   rc = xa_make_tmap(&tk, k, b, Lk, heads * dh, ldk, XA_KT);
@@ -346,11 +350,11 @@ int xattn_mma_fwd(const void* q, const void* k, const void* v, void* o, float* l
 // Phase 1 (before the wait on the Q/dO barrier) fills ov, phase 2 (after it) reduces.
 template <int NCH>
 __device__ __forceinline__ void delta_load_o(uint4 (&ov)[16], const __nv_bfloat16* __restrict__ o, int warp, int lane,
-                                             int b, int h, int Lq, int HD) {
+                                             int b, int h, int Lq, int HD, int q0 = 0) {
   const bool act = lane < NCH * 8;
 #pragma unroll
   for (int rr = 0; rr < 16; ++rr) {
-    const int row = warp * 16 + rr;
+    const int row = q0 + warp * 16 + rr;
     ov[rr] = make_uint4(0u, 0u, 0u, 0u);
     if (act && row < Lq)
       ov[rr] = __ldg(reinterpret_cast<const uint4*>(o + ((size_t)b * Lq + row) * HD + h * (NCH * 64) + lane * 8));
@@ -358,7 +362,7 @@ __device__ __forceinline__ void delta_load_o(uint4 (&ov)[16], const __nv_bfloat1
 }
 template <int NCH>
 __device__ __forceinline__ void delta_reduce(const uint4 (&ov)[16], uint32_t do_base, int qrows, int warp, int lane,
-                                             int Lq, float* delta_s, float* delta_g) {
+                                             int Lq, float* delta_s, float* delta_g, int q0 = 0) {
   const bool act = lane < NCH * 8;
 #pragma unroll
   for (int rr = 0; rr < 16; ++rr) {
@@ -380,7 +384,7 @@ __device__ __forceinline__ void delta_reduce(const uint4 (&ov)[16], uint32_t do_
     sacc = warp_sum(sacc);
     if (lane == 0) {
       delta_s[row] = sacc;
-      if (delta_g != nullptr && row < Lq) delta_g[row] = sacc;
+      if (delta_g != nullptr && q0 + row < Lq) delta_g[q0 + row] = sacc;
     }
   }
   __syncwarp();
@@ -418,6 +422,7 @@ xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  const int q0 = blockIdx.y * QROWS;                    // query chunk of this CTA (query sets of more than 64 rows)
   const int dh = NCH * 64, HD = heads * dh;
   const int num_tiles = (Lk + XA_KT - 1) / XA_KT;
 
@@ -445,16 +450,16 @@ xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_arrive_expect_tx(qb, 2 * q_bytes);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
-      tma_load_3d(smem_u32(Qs) + c * QROWS * 128, &tmQ, qb, h * dh + c * 64, 0, b);
-      tma_load_3d(smem_u32(dOs) + c * QROWS * 128, &tmDO, qb, h * dh + c * 64, 0, b);
+      tma_load_3d(smem_u32(Qs) + c * QROWS * 128, &tmQ, qb, h * dh + c * 64, q0, b);
+      tma_load_3d(smem_u32(dOs) + c * QROWS * 128, &tmDO, qb, h * dh + c * 64, q0, b);
     }
     issue_tile(0);
   }
   {
     uint4 ov[16];
-    delta_load_o<NCH>(ov, o, warp, lane, b, h, Lq, HD);
+    delta_load_o<NCH>(ov, o, warp, lane, b, h, Lq, HD, q0);
     mbar_wait(smem_u32(&bars[0]), 0);
-    delta_reduce<NCH>(ov, smem_u32(dOs), QROWS, warp, lane, Lq, delta_s, delta + (size_t)bh * Lq);
+    delta_reduce<NCH>(ov, smem_u32(dOs), QROWS, warp, lane, Lq, delta_s, delta + (size_t)bh * Lq, q0);
   }
 
   const int g = lane >> 2, t4 = lane & 3;
@@ -463,7 +468,7 @@ xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int row = row0 + r * 8;
-    lse2[r] = (row < Lq) ? lse[(size_t)bh * Lq + row] * kLog2e : INFINITY;
+    lse2[r] = (q0 + row < Lq) ? lse[(size_t)bh * Lq + q0 + row] * kLog2e : INFINITY;
     dl[r] = delta_s[row];
   }
   float qacc[NCH * 8][4];
@@ -510,7 +515,8 @@ xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     const int key0 = t * XA_KT;
     uint32_t keep[2] = {0xffffffffu, 0xffffffffu};
-    if (p_drop > 0.f) dropout_bits_tile(keep, seed, offset, (uint64_t)bh * Lq + row0, key0, (Lk + 3) >> 2, drop_thr, t4);
+    if (p_drop > 0.f)
+      dropout_bits_tile(keep, seed, offset, (uint64_t)bh * Lq + q0 + row0, key0, (Lk + 3) >> 2, drop_thr, t4);
 #pragma unroll
     for (int i = 0; i < XA_KT / 8; ++i) {
 #pragma unroll
@@ -543,7 +549,7 @@ xattn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    const int row = row0 + r * 8;
+    const int row = q0 + row0 + r * 8;
     if (row >= Lq) continue;
     __nv_bfloat16* orow = dq + ((size_t)b * Lq + row) * HD + h * dh;
 #pragma unroll
@@ -684,6 +690,171 @@ xattn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
     __nv_bfloat16* outp = pass == 0 ? dv : dk;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int key = key_lo + r * 8;
+      if (key >= Lk) continue;
+      __nv_bfloat16* orow = outp + ((size_t)b * Lk + key) * HD + h * dh;
+#pragma unroll
+      for (int i = 0; i < NCH * 8; ++i)
+        *reinterpret_cast<uint32_t*>(orow + i * 8 + t4 * 2) = pack_bf16(acc[i][2 * r], acc[i][2 * r + 1]);
+    }
+  }
+}
+
+// =============================================================================================================
+// dK / dV for query sets of MORE than 64 rows (the TQN fusion head attends with Lq = B queries per sample,
+// reference CAR_heads/transformer_decoder.py:146-240 via model.py:552-561): one CTA per (sample, head, 64-key tile)
+// keeps its K / V tile in shared memory and LOOPS over the queries in chunks of 64 rows (Q / dO chunk by TMA), so the
+// whole backward of any Lq is two launches (this kernel + the chunked dQ kernel) and dK / dV are complete per CTA --
+// no atomics, no per-chunk partial gradients to add up on the host.  Two sweeps over the chunks with ONE accumulator
+// set (registers): sweep 0 accumulates dV = Pd^T dO, sweep 1 dK = dS^T Q.
+template <int NCH>
+__global__ void __launch_bounds__(128)
+xattn_bwd_dkv_loop_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                          const float* __restrict__ lse, const float* __restrict__ delta,
+                          __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv,
+                          int Lq, int Lk, int heads, int tiles_per_bh, float sl2, float sm_scale, float p_drop,
+                          uint64_t seed, uint64_t offset) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int NQT = 4, QROWS = 64;
+  constexpr uint32_t q_bytes = (uint32_t)NCH * QROWS * 128;
+  constexpr uint32_t kv_chunk = XA_KTB * 128;
+  uint8_t* Qs = smem;
+  uint8_t* dOs = smem + q_bytes;
+  uint8_t* Ks = smem + 2 * q_bytes;
+  uint8_t* Vs = Ks + NCH * kv_chunk;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + NCH * kv_chunk);      // [0] K/V tile, [1] Q/dO chunk
+  float* lse2_s = reinterpret_cast<float*>(bars + 2);
+  float* delta_s = lse2_s + QROWS;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int bh = blockIdx.x / tiles_per_bh, kt = blockIdx.x % tiles_per_bh;
+  const int b = bh / heads, h = bh % heads;
+  const int dh = NCH * 64, HD = heads * dh;
+  const int key_base = kt * XA_KTB;
+  const int nchunks = (Lq + QROWS - 1) / QROWS;
+
+  if (tid == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV); prefetch_tmap(&tmDO);
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t fb = smem_u32(&bars[0]);
+    mbar_arrive_expect_tx(fb, 2 * NCH * kv_chunk);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      tma_load_3d(smem_u32(Ks) + c * kv_chunk, &tmK, fb, h * dh + c * 64, key_base, b);
+      tma_load_3d(smem_u32(Vs) + c * kv_chunk, &tmV, fb, h * dh + c * 64, key_base, b);
+    }
+  }
+  mbar_wait(smem_u32(&bars[0]), 0);
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const uint32_t q_base = smem_u32(Qs), do_base = smem_u32(dOs), k_base = smem_u32(Ks), v_base = smem_u32(Vs);
+  const int krow_a = warp * 16 + (lane & 15);
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const uint32_t drop_thr = philox_drop_threshold(p_drop);
+  const int key_lo = key_base + warp * 16 + g;
+  uint32_t load_idx = 0;
+
+#pragma unroll 1
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    float acc[NCH * 8][4];
+#pragma unroll
+    for (int i = 0; i < NCH * 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 1
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int q0 = ch * QROWS;
+      __syncthreads();                                   // every warp is done with the previous chunk's tiles
+      if (tid == 0) {
+        const uint32_t fb = smem_u32(&bars[1]);
+        mbar_arrive_expect_tx(fb, 2 * q_bytes);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          tma_load_3d(q_base + c * QROWS * 128, &tmQ, fb, h * dh + c * 64, q0, b);
+          tma_load_3d(do_base + c * QROWS * 128, &tmDO, fb, h * dh + c * 64, q0, b);
+        }
+      }
+      for (int i = tid; i < QROWS; i += blockDim.x) {
+        lse2_s[i] = (q0 + i < Lq) ? lse[(size_t)bh * Lq + q0 + i] * kLog2e : INFINITY;      // padded queries: P = 0
+        delta_s[i] = (q0 + i < Lq) ? delta[(size_t)bh * Lq + q0 + i] : 0.f;
+      }
+      __syncthreads();
+      mbar_wait(smem_u32(&bars[1]), load_idx & 1u);
+      ++load_idx;
+
+      // S^T = K_w Q^T (and, for dK, dP^T = V_w dO^T): 16 keys x 64 queries
+      float st[2 * NQT][4], pt[2 * NQT][4];
+#pragma unroll
+      for (int i = 0; i < 2 * NQT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { st[i][j] = 0.f; pt[i][j] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < NCH * 4; ++kk) {
+        const int c = kk >> 2, kx = (kk & 3) * 16;
+        uint32_t ak[4], av[4];
+        ldsm_x4(k_base + c * kv_chunk + swz(krow_a, kx + ((lane >> 4) << 3)), ak);
+        if (sweep == 1) ldsm_x4(v_base + c * kv_chunk + swz(krow_a, kx + ((lane >> 4) << 3)), av);
+#pragma unroll
+        for (int np = 0; np < NQT; ++np) {
+          const int qr = np * 16 + ((lane >> 4) << 3) + (lane & 7);
+          const int qc = kx + (((lane >> 3) & 1) << 3);
+          uint32_t bq[4];
+          ldsm_x4(q_base + c * QROWS * 128 + swz(qr, qc), bq);
+          mma_bf16(st[2 * np], ak, bq[0], bq[1]);
+          mma_bf16(st[2 * np + 1], ak, bq[2], bq[3]);
+          if (sweep == 1) {
+            uint32_t bd[4];
+            ldsm_x4(do_base + c * QROWS * 128 + swz(qr, qc), bd);
+            mma_bf16(pt[2 * np], av, bd[0], bd[1]);
+            mma_bf16(pt[2 * np + 1], av, bd[2], bd[3]);
+          }
+        }
+      }
+      // elementwise: rows = keys (g, g+8), columns = queries; st <- the A operand of this sweep's product
+#pragma unroll
+      for (int i = 0; i < 2 * NQT; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int qi = i * 8 + t4 * 2 + (j & 1);
+          const int key = key_base + warp * 16 + g + ((j >> 1) << 3);
+          const float p = fast_exp2(fmaf(st[i][j], sl2, -lse2_s[qi]));
+          float m = 1.f;
+          if (p_drop > 0.f) {
+            m = (q0 + qi < Lq && key < Lk &&
+                 philox_keep(seed, offset, (uint64_t)bh * Lq + q0 + qi, key, (Lk + 3) >> 2, drop_thr))
+                    ? keep_scale : 0.f;
+          }
+          st[i][j] = (sweep == 0) ? p * m                                          // Pd^T
+                                  : p * (pt[i][j] * m - delta_s[qi]) * sm_scale;   // dS^T
+        }
+      }
+      const uint32_t b_base = sweep == 0 ? do_base : q_base;
+#pragma unroll
+      for (int ks = 0; ks < NQT; ++ks) {
+        uint32_t a[4];
+        a[0] = pack_bf16(st[2 * ks][0], st[2 * ks][1]);         a[1] = pack_bf16(st[2 * ks][2], st[2 * ks][3]);
+        a[2] = pack_bf16(st[2 * ks + 1][0], st[2 * ks + 1][1]); a[3] = pack_bf16(st[2 * ks + 1][2], st[2 * ks + 1][3]);
+#pragma unroll
+        for (int dn = 0; dn < NCH * 4; ++dn) {
+          const int qr = ks * 16 + (((lane >> 3) & 1) << 3) + (lane & 7);
+          const int dc = dn * 16 + ((lane >> 4) << 3);
+          uint32_t bb[4];
+          ldsm_x4_t(b_base + (dc >> 6) * QROWS * 128 + swz(qr, dc & 63), bb);
+          mma_bf16(acc[2 * dn], a, bb[0], bb[1]);
+          mma_bf16(acc[2 * dn + 1], a, bb[2], bb[3]);
+        }
+      }
+    }
+    __nv_bfloat16* outp = sweep == 0 ? dv : dk;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int key = key_lo + r * 8;
@@ -1068,12 +1239,61 @@ static int launch_bwd(const void* q, const void* k, const void* v, const void* o
 }
 
 // delta_ws: caller scratch of b*heads*Lq floats
+// Backward for query sets of more than 64 rows: the chunked dQ kernel + the looping dK / dV kernel (two launches).
+template <int NCH>
+static int launch_bwd_loop(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                           void* dq, void* dk, void* dv, float* delta, int b, int Lq, int Lk, int heads, int ldq, int ldk,
+                           int ldv, float sm_scale, float p, uint64_t seed, uint64_t offset, cudaStream_t st) {
+  const int dh = NCH * 64, HD = heads * dh;
+  const int nw = XA_MAXW;
+  const float sl2 = sm_scale * kLog2e;
+  CUtensorMap tq, tdo, tk, tv, tk2, tv2;
+  int rc;
+  if ((rc = xa_make_tmap(&tq, q, b, Lq, HD, ldq, 16 * nw))) return rc;
+  if ((rc = xa_make_tmap(&tdo, d_o, b, Lq, HD, HD, 16 * nw))) return rc;
+  if ((rc = xa_make_tmap(&tk, k, b, Lk, HD, ldk, XA_KT))) return rc;
+  if ((rc = xa_make_tmap(&tv, v, b, Lk, HD, ldv, XA_KT))) return rc;
+  if ((rc = xa_make_tmap(&tk2, k, b, Lk, HD, ldk, XA_KTB))) return rc;
+  if ((rc = xa_make_tmap(&tv2, v, b, Lk, HD, ldv, XA_KTB))) return rc;
+  XTAG_CUDA(sync_spin_timeout());
+  {
+    const size_t q_pad = ((size_t)NCH * 16 * nw * 128 + 1023) & ~(size_t)1023;
+    const size_t smem = 1024 + 2 * q_pad + 2 * (2 * NCH * XA_KT * 128) + 64 + 16 * nw * 4;
+    XTAG_CUDA(cudaFuncSetAttribute(xattn_bwd_dq_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 grid((unsigned)(b * heads), (unsigned)((Lq + 16 * nw - 1) / (16 * nw)));
+    xattn_bwd_dq_kernel<NCH><<<grid, 32 * nw, smem, st>>>(tq, tk, tv, tdo, (const __nv_bfloat16*)o,
+                                                          (const __nv_bfloat16*)d_o, lse, (__nv_bfloat16*)dq, delta, Lq, Lk,
+                                                          heads, sl2, sm_scale, p, seed, offset);
+    XTAG_CHECK_LAUNCH();
+  }
+  {
+    const int tiles = (Lk + XA_KTB - 1) / XA_KTB;
+    const size_t smem = 1024 + 2 * (size_t)NCH * 64 * 128 + 2 * (size_t)NCH * XA_KTB * 128 + 64 + 2 * 64 * 4;
+    XTAG_CUDA(cudaFuncSetAttribute(xattn_bwd_dkv_loop_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    xattn_bwd_dkv_loop_kernel<NCH><<<b * heads * tiles, 128, smem, st>>>(tq, tk2, tv2, tdo, lse, delta, (__nv_bfloat16*)dk,
+                                                                         (__nv_bfloat16*)dv, Lq, Lk, heads, tiles, sl2,
+                                                                         sm_scale, p, seed, offset);
+    XTAG_CHECK_LAUNCH();
+  }
+  return XTAG_OK;
+}
+
 int xattn_mma_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                   void* dq, void* dk, void* dv, float* delta_ws, int b, int Lq, int Lk, int heads, int dh, int ldq, int ldk,
                   int ldv, int lddk, int lddv, float sm_scale, float p_drop, uint64_t seed, uint64_t offset,
                   cudaStream_t st) {
   // the single-pass kernel keeps dQ [16 x dh] and one [32 x dh/NW] product tile per warp in registers: shapes whose
   // accumulators would spill (few warps with a wide head) stay on the two-kernel path
+  if (Lq > 16 * XA_MAXW) {
+    XTAG_REQUIRE(lddk == heads * dh && lddv == heads * dh, XTAG_ERR_UNSUPPORTED,
+                 "xattn_bwd: strided dK / dV outputs are not supported for query sets of more than %d rows", 16 * XA_MAXW);
+    switch (dh / 64) {
+      case 1: return launch_bwd_loop<1>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+      case 2: return launch_bwd_loop<2>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+      case 3: return launch_bwd_loop<3>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+      default: return launch_bwd_loop<4>(q, k, v, o, d_o, lse, dq, dk, dv, delta_ws, b, Lq, Lk, heads, ldq, ldk, ldv, sm_scale, p_drop, seed, offset, st);
+    }
+  }
   const int nw = (Lq + 15) / 16, nch = dh / 64;
   const int acc_regs = 16 * ((nch * 4 + nw - 1) / nw) + 32 * nch;
   if ((tc_tune() & kTuneXattnFusedBwd) && acc_regs <= 224) {

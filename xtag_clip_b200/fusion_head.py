@@ -29,7 +29,7 @@ import torch.nn.functional as F
 
 from .tag_head import cross_attention
 
-Q_CHUNK = 64          # K4's tensor-core path holds <= 64 query rows per CTA
+Q_CHUNK = 64          # the exact fp32 K4 kernels hold the whole [Lq, Lk] score block of a (sample, head) in shared memory
 _LOG2E = 1.4426950408889634
 
 
@@ -104,6 +104,11 @@ class FusionHead(nn.Module):
         E = self.d_model
         k, v = kv[..., :E], kv[..., E:]
         drop = self.p_drop if self.training else 0.0
+        if q.is_cuda and q.dtype == torch.bfloat16 and (E // self.nhead) in (64, 128, 192, 256):
+            # tensor-core K4 takes a query set of any length in ONE launch (64-row chunks on the grid; the backward is
+            # the chunked dQ kernel + the dK / dV kernel that loops over the query chunks: no per-chunk partial
+            # gradients to add up)
+            return cross_attention(q, k, v, self.nhead, drop, seed, offset * 64, _kernels=self._k)
         out = []
         for ci, c in enumerate(range(0, q.shape[1], Q_CHUNK)):
             out.append(cross_attention(q[:, c:c + Q_CHUNK], k, v, self.nhead, drop, seed, offset * 64 + ci,
