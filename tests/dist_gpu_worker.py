@@ -103,17 +103,17 @@ def main():
         lg = xt.ClipLoss()(Ig, Tg, sg)
         lg.backward()
         lo, hi = rank * b, (rank + 1) * b
-        for exch in ("pull", "push"):
+        for exch, ps in (("pull", 2), ("pull", 1), ("push", 2)):      # ps: copy streams of the exchange (default 2)
             for cg in (False, True):
                 mod = xt.ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world, exchange=exch,
-                                  cuda_graph=cg)
+                                  cuda_graph=cg, pull_streams=ps)
                 for it in range(3 if cg else 2):        # replays after the capture; slot parity of the eager path
                     I = I_all[lo:hi].to(dev).requires_grad_(True)
                     T = T_all[lo:hi].to(dev).requires_grad_(True)
                     s = torch.tensor(14.285714, device=dev, requires_grad=True)
                     loss = mod(I, T, s)
                     loss.backward()
-                    tag = f"{name} b={b} D={D} W={world} {exch} graph={cg} it={it} rank={rank}"
+                    tag = f"{name} b={b} D={D} W={world} {exch}/{ps} graph={cg} it={it} rank={rank}"
                     lm = loss.detach().clone()
                     dist.all_reduce(lm)
                     lm /= world

@@ -162,7 +162,7 @@ class _Cfg:
     pipeline: bool = True
     symm: bool = True
     stream_fwd: bool = True
-    pull_streams: int = 1
+    pull_streams: int = 2
     exchange: str = "pull"
     will_backward: bool = True       # a backward of this forward is expected (grad mode on, some input requires grad)
     gather_buf: Optional[torch.Tensor] = None   # captured steps: the symmetric gather buffer (symm.make_graph_gather)
@@ -584,7 +584,7 @@ class ClipLoss(nn.Module):
             pipeline: bool = True,
             symmetric_memory: bool = True,
             stream_forward: bool = True,
-            pull_streams: int = 1,
+            pull_streams: int = 2,
             exchange: Optional[str] = None,
             cuda_graph: bool = False,
             compute_dtype: Optional[torch.dtype] = None,

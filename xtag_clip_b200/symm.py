@@ -152,9 +152,9 @@ class SymmExchange:
         step's epoch into its ready flag.  Returns (order, wait) for `clip_fwd_stream`: the persistent K1 launch on the
         compute stream starts with the rank's own block and picks up each peer block the moment its flag flips -- no
         event waits, no launch per block.  `end_gather` joins the copy stream(s) afterwards.
-        pull_streams = 1 (validated default): all pulls on ONE copy stream -- a fixed arrival order, but the flag copy
+        pull_streams = 1: all pulls on ONE copy stream -- a fixed arrival order, but the flag copy
         and the scheduling gaps around it sit between consecutive block copies (measured: 28 us per 8 MiB block of which
-        17 us is the copy).  pull_streams = 2: blocks alternate between two copy streams so that one stream's flag
+        17 us is the copy).  pull_streams = 2 (default of ClipLoss): blocks alternate between two copy streams so that one stream's flag
         copy and gaps hide behind the other stream's block copy (K1's correctness does not depend on the arrival
         order: it waits per block)."""
         b, s, W, r = self.b, self.slot, self.W, self.r
