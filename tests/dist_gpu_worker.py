@@ -142,7 +142,9 @@ def main():
         if it == 1 and rank == world - 1:
             torch.cuda.synchronize()
             import time
-            time.sleep(1.5)
+            # XTAG_LONG_SKEW_S=70 (opt-in, with XTAG_SPIN_TIMEOUT_MS unset or larger): a rank that stalls for over a
+            # minute -- data-loader hiccup, rank-0-only checkpoint -- must not trap the waiting ranks
+            time.sleep(float(os.environ.get("XTAG_LONG_SKEW_S", "1.5")))
         I = I_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
         T = T_all[rank * b:(rank + 1) * b].to(dev).requires_grad_(True)
         loss = mod(I, T, torch.tensor(14.285714, device=dev))
