@@ -264,6 +264,11 @@ int xtag_asl_fwd(const void* x, int x_dtype, const float* y, int rows, int cols,
 int xtag_debug_tile_coords(int M, int N, int slab, const int* order_host, int tile,
                            int* m_blk, int* n_blk, int* slab_idx);
 int xtag_debug_pick_cluster(int M, int N, int tune);
+/* work item -> (m block, n tile, K slice) of the CTA-pair kernels (rows_per_tile = 256: m_blk counts 256-row blocks)
+ * or the single-CTA kernels (128), with the schedule's group size (0 = default; 1 = the n-fastest order of plain GEMMs
+ * with few n tiles) and split-K (item = tile * split_k + slice) */
+int xtag_debug_work_item(int M, int N, int rows_per_tile, int slab, int group_m, int split_k, int item,
+                         int* m_blk, int* n_blk, int* k_slice);
 
 /* ---- symmetric cross-entropy on a materialised square score matrix: DQNCOSLoss of the TQN fusion head ---------
  * (reference src/open_clip/tagging_heads/asymmetric_loss.py:54-65;  SURVEY.md section 8f rank 2)

@@ -84,3 +84,32 @@ def test_streamed_forward_walks_blocks_in_arrival_order(lib, W, b, M):
             blocks = [coords(lib, M, N, blk_tiles, order, t)[1] // blk_tiles for t in range(cta, num_m * num_n, 148)]
             dedup = [k for k, _ in itertools.groupby(blocks)]
             assert dedup == [blk for blk in order if blk in dedup] and len(set(dedup)) == len(dedup)
+
+
+def work_item(lib, M, N, rows, slab, group, split, item):
+    m, n, k = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = lib.xtag_debug_work_item(M, N, rows, slab, group, split, item, ctypes.byref(m), ctypes.byref(n), ctypes.byref(k))
+    assert rc == 0
+    return m.value, n.value, k.value
+
+
+@pytest.mark.parametrize("M,N", [(32768, 1024), (4096, 768), (330, 1320), (130, 300), (8192, 32768 // 8)])
+@pytest.mark.parametrize("rows", [128, 256])
+@pytest.mark.parametrize("group,split", [(0, 1), (1, 1), (1, 3), (0, 8), (5, 2)])
+def test_pair_schedule_group_and_split_k_cover_every_work_item_once(lib, M, N, rows, group, split):
+    """CTA-pair tiles (256 rows), the n-fastest order of the gradient GEMMs (group 1) and split-K work items: every
+    (tile, K slice) exactly once; with group 1 the n tiles of one m block are consecutive; the K slices of a tile are
+    adjacent work items (they run side by side)."""
+    num_m, num_n = -(-M // rows), -(-N // BN)
+    items = [work_item(lib, M, N, rows, 32, group, split, i) for i in range(num_m * num_n * split)]
+    assert len(set(items)) == num_m * num_n * split
+    assert all(0 <= m < num_m and 0 <= n < num_n and 0 <= k < split for m, n, k in items)
+    for t in range(num_m * num_n):                                  # slices of one tile are consecutive
+        sl = items[t * split:(t + 1) * split]
+        assert len({(m, n) for m, n, _ in sl}) == 1 and [k for _, _, k in sl] == list(range(split))
+    if group == 1 and num_n <= 32:
+        tiles_only = items[::split]
+        for mi in range(num_m):                                     # n-fastest: one m block, all its n tiles in a row
+            run = tiles_only[mi * num_n:(mi + 1) * num_n]
+            assert {m for m, _, _ in run} == {mi} and [n for _, n, _ in run] == list(range(num_n))
+    assert lib.xtag_debug_work_item(M, N, 64, 0, 0, 1, 0, None, None, None) != 0

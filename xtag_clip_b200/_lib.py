@@ -72,6 +72,7 @@ SIGNATURES = {
                                c_float, c_float, c_uint64, c_uint64, c_void_p, c_size_t, c_void_p]),
     "xtag_debug_tile_coords": (c_int, [c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "xtag_debug_pick_cluster": (c_int, [c_int, c_int, c_int]),
+    "xtag_debug_work_item": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "xtag_siglip_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float,
                                 c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "xtag_symm_ce_ws_bytes": (c_size_t, [c_int]),

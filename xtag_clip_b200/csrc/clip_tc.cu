@@ -1449,5 +1449,21 @@ extern "C" int xtag_debug_tile_coords(int M, int N, int slab, const int* order, 
   return XTAG_OK;
 }
 
+// Same for the CTA-pair kernels and the plain-GEMM variants: `rows_per_tile` = 128 (single CTA) or 256 (CTA pair: the
+// returned m_blk counts 256-row blocks), group_m = m tiles per schedule group (0 = default, 1 = n-fastest order of the
+// gradient GEMMs), split_k = K slices per tile (work item = tile * split_k + slice).
+extern "C" int xtag_debug_work_item(int M, int N, int rows_per_tile, int slab, int group_m, int split_k, int item,
+                                    int* m_blk, int* n_blk, int* k_slice) {
+  if (M <= 0 || N <= 0 || (rows_per_tile != BM && rows_per_tile != 2 * BM) || !m_blk || !n_blk) return XTAG_ERR_INVALID;
+  const int S = split_k > 1 ? split_k : 1;
+  const int num_m = (M + rows_per_tile - 1) / rows_per_tile, num_n = (N + BN - 1) / BN;
+  if (item < 0 || item >= num_m * num_n * S) return XTAG_ERR_INVALID;
+  const int sl = (slab > 0 && slab < num_n) ? slab : num_n;
+  const int grp = group_m > 0 ? group_m : kGroupM / (rows_per_tile / BM);
+  tile_coords(item / S, num_m, num_n, sl, nullptr, *m_blk, *n_blk, nullptr, grp);
+  if (k_slice) *k_slice = item % S;
+  return XTAG_OK;
+}
+
 // cluster size the launcher would pick for an [M, N] problem under tuning bits `tune`
 extern "C" int xtag_debug_pick_cluster(int M, int N, int tune) { return pick_cluster(M, N, tune); }
