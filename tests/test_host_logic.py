@@ -238,3 +238,34 @@ def test_tag_head_golden_and_state_dict(golden_dir):
         assert head.prepare_control_words(logits.detach()) == list(g[pre + "words"])
     with pytest.raises(ValueError):
         head.tag_forward(torch.randn(2, 5, int(D) + 1, dtype=torch.float64))
+
+
+def test_siglip_w1_host_logic_vs_reference_fixture(golden_dir):
+    """SigLipLoss (single process) with the contract-model kernels against what the reference's SigLipLoss produced
+    (tests/golden/siglip.npz): value, feature / scale / bias gradients, upstream-gradient scaling, output_dict, and the
+    no-grad path that skips staging the logit gradient."""
+    g = _load(golden_dir, "siglip.npz")
+    for n in range(int(g["n_w1"])):
+        pre = f"w1_{n}_"
+        k = ModelKernels()
+        I = torch.from_numpy(g[pre + "I"]).clone().requires_grad_(True)
+        T = torch.from_numpy(g[pre + "T"]).clone().requires_grad_(True)
+        s = torch.tensor(float(g[pre + "scale"]), dtype=torch.float64, requires_grad=True)
+        b = torch.tensor(float(g[pre + "bias"]), dtype=torch.float64, requires_grad=True)
+        out = xt.SigLipLoss(compute_dtype=torch.bfloat16, _kernels=k)(I, T, s, b, output_dict=True)
+        assert list(out) == ["contrastive_loss"]
+        (out["contrastive_loss"] * 2.0).backward()
+        # the drop-in rounds the features to bf16 (its compute dtype); the fixture is the reference's fp64 run
+        assert rel_err(out["contrastive_loss"].item(), float(g[pre + "loss"])) < 2e-2
+        assert rel_err(I.grad.numpy(), 2.0 * g[pre + "dI"]) < 3e-2 and rel_err(T.grad.numpy(), 2.0 * g[pre + "dT"]) < 3e-2
+        assert abs(float(s.grad) - 2.0 * float(g[pre + "dscale"])) <= 3e-2 * abs(2.0 * float(g[pre + "dscale"])) + 1e-6
+        assert abs(float(b.grad) - 2.0 * float(g[pre + "dbias"])) <= 3e-2 * abs(2.0 * float(g[pre + "dbias"])) + 1e-6
+        assert [c[0] for c in k.calls] == ["siglip_fwd", "clip_bwd"]
+    with torch.no_grad():
+        k = ModelKernels()
+        xt.SigLipLoss(compute_dtype=torch.bfloat16, _kernels=k)(I.detach(), T.detach(), 10.0, -10.0)
+        assert [c[0] for c in k.calls] == ["siglip_fwd"]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        xt.SigLipLoss()(I.detach(), T.detach(), 10.0, -10.0)
+    with pytest.raises(NotImplementedError):
+        xt.SigLipLoss(_kernels=ModelKernels())(I.detach().float(), T.detach().float(), 10.0, -10.0)   # fp32, no autocast
