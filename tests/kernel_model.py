@@ -179,13 +179,61 @@ class ModelKernels:
         o, lse = self._attn(_f64(q), _f64(k), _f64(v), heads, softmax_scale)
         return o.to(q.dtype), lse.float()
 
-    def xattn_bwd(self, q, k, v, o, do, lse, heads, softmax_scale, dropout_p, seed, offset):
+    def xattn_bwd(self, q, k, v, o, do, lse, heads, softmax_scale, dropout_p, seed, offset, dk_out=None, dv_out=None):
+        if dk_out is not None:
+            return self.xattn_bwd_into(q, k, v, o, do, lse, heads, softmax_scale, dropout_p, seed, offset, dk_out, dv_out)
         assert dropout_p == 0.0
         q64, k64, v64 = (_f64(t).requires_grad_(True) for t in (q, k, v))
         with torch.enable_grad():
             out, _ = self._attn(q64, k64, v64, heads, softmax_scale)
             out.backward(_f64(do))
         return q64.grad.to(q.dtype), k64.grad.to(q.dtype), v64.grad.to(q.dtype)
+
+    def xattn_bwd_into(self, q, k, v, o, do, lse, heads, softmax_scale, dropout_p, seed, offset, dk_out, dv_out):
+        dq, dk, dv = self.xattn_bwd(q, k, v, o, do, lse, heads, softmax_scale, dropout_p, seed, offset)
+        dk_out.copy_(dk)
+        dv_out.copy_(dv)
+        return dq, dk_out, dv_out
+
+    # dense layer with bias epilogue (xtag_tc_linear_bf16) and the plain GEMM (xtag_tc_gemm_ex)
+    def tc_linear(self, x2d, weight, bias):
+        self.calls.append(("tc_linear", tuple(x2d.shape), tuple(weight.shape)))
+        y = _f64(x2d) @ _f64(weight).T
+        if bias is not None:
+            y = y + _f64(bias)
+        return y.to(torch.bfloat16)
+
+    def tc_gemm(self, A, B, a_mn, b_mn, out_dtype=torch.float32, alpha=1.0):
+        self.calls.append(("tc_gemm", tuple(A.shape), tuple(B.shape), bool(a_mn), bool(b_mn)))
+        A64 = _f64(A).T if a_mn else _f64(A)          # -> [M, K]
+        B64 = _f64(B).T if b_mn else _f64(B)          # -> [N, K]
+        return (alpha * (A64 @ B64.T)).to(out_dtype)
+
+    # K6: y = LayerNorm(dropout(x) + resid) (eval mode in the contract model)
+    def supports_ln_res(self, H):
+        return True
+
+    def ln_res_fwd(self, x, resid, gamma, beta, eps, dropout_p, seed, offset):
+        assert dropout_p == 0.0, "the contract model covers eval mode"
+        self.calls.append(("ln_res_fwd", tuple(x.shape), tuple(resid.shape)))
+        rows = x.shape[0]
+        z = _f64(x) + _f64(resid).repeat(rows // resid.shape[0], 1)
+        mean = z.mean(-1)
+        rstd = 1.0 / torch.sqrt(z.var(-1, unbiased=False) + eps)
+        y = (z - mean[:, None]) * rstd[:, None] * _f64(gamma) + _f64(beta)
+        return y.to(torch.bfloat16), z.to(torch.bfloat16), mean.float(), rstd.float()
+
+    def ln_res_bwd(self, dy, z, mean, rstd, gamma, dropout_p, seed, offset):
+        assert dropout_p == 0.0
+        self.calls.append(("ln_res_bwd", tuple(z.shape)))
+        H = z.shape[1]
+        d = _f64(dy).reshape(-1, H)
+        xh = (_f64(z) - _f64(mean)[:, None]) * _f64(rstd)[:, None]
+        dg, db = (d * xh).sum(0), d.sum(0)
+        dyg = d * _f64(gamma)
+        dz = _f64(rstd)[:, None] * (dyg - dyg.mean(-1, keepdim=True) - xh * (dyg * xh).mean(-1, keepdim=True))
+        dzb = dz.to(torch.bfloat16)
+        return dzb, dzb.clone(), dg.float(), db.float()
 
     # K5
     def asl(self, x, y, gamma_neg, gamma_pos, clip, eps, want_dx, want_idx):

@@ -269,3 +269,37 @@ def test_siglip_w1_host_logic_vs_reference_fixture(golden_dir):
         xt.SigLipLoss()(I.detach(), T.detach(), 10.0, -10.0)
     with pytest.raises(NotImplementedError):
         xt.SigLipLoss(_kernels=ModelKernels())(I.detach().float(), T.detach().float(), 10.0, -10.0)   # fp32, no autocast
+
+
+def test_tag_head_fused_paths_host_logic():
+    """The production plumbing of the tag head (one fused K|V projection for both layers, K4 reading / writing column
+    slices of shared buffers, K6 dense-output blocks, projection backward on the package's GEMMs) with the contract
+    model on CPU, bf16, against the library path of the same head (one Linear per projection, torch LayerNorm):
+    logits and the gradients of tokens, projection weights / biases, LayerNorm parameters and the label embeddings."""
+    torch.manual_seed(0)
+    D, b, N = 64, 3, 7
+    params = make_tag_params(3, D, gain=4.0, dtype=torch.float32)
+    g = torch.Generator().manual_seed(1)
+    tokens = torch.randn(b, N, D, generator=g)
+    wgt = torch.randn(b, 44, generator=g)
+    outs, calls = [], []
+    for fused in (True, False):
+        k = ModelKernels()
+        head = xt.TagHead(D, fuse_kv=fused, fuse_ln=fused, _kernels=k)
+        head.load_state_dict(params, strict=True)
+        head = head.bfloat16().eval()
+        tok = tokens.bfloat16().requires_grad_(True)
+        logits = head.tag_forward(tok)
+        (logits.float() * wgt).sum().backward()
+        L = head.tag_head.encoder.layer
+        outs.append([logits.float().detach(), tok.grad.float(),
+                     L[1].crossattention.self.key.weight.grad.float(), L[0].crossattention.self.value.bias.grad.float(),
+                     L[0].crossattention.output.LayerNorm.weight.grad.float(), L[1].output.LayerNorm.bias.grad.float(),
+                     head.tag_labels.weight.grad.float()])
+        calls.append([c[0] for c in k.calls])
+    for a, c in zip(outs[0], outs[1]):
+        assert rel_err(a.numpy(), c.numpy()) < 6e-2, rel_err(a.numpy(), c.numpy())
+    fused_calls = calls[0]
+    assert fused_calls.count("tc_linear") == 1 and fused_calls.count("tc_gemm") == 2      # projection fwd; dX and dW
+    assert fused_calls.count("ln_res_fwd") == 4 and fused_calls.count("ln_res_bwd") == 4
+    assert "tc_linear" not in calls[1] and "ln_res_fwd" not in calls[1]

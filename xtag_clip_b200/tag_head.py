@@ -307,7 +307,8 @@ class TagHead(nn.Module):
         amp_bf16 = tag_embeds.is_cuda and torch.is_autocast_enabled("cuda") and \
             torch.get_autocast_dtype("cuda") == torch.bfloat16
         fused_kv = None
-        if self.fuse_kv and tag_embeds.is_cuda and self.embed_dim % 8 == 0 and \
+        hooked = self._k is not None                 # injected kernel provider (the CPU contract model of the tests)
+        if self.fuse_kv and (tag_embeds.is_cuda or hooked) and self.embed_dim % 8 == 0 and \
                 (tag_embeds.dtype == torch.bfloat16 or amp_bf16) and \
                 hasattr(_kernels(self._k), "tc_linear"):
             w = torch.cat([m.weight for l in layers for m in (l.crossattention.self.key, l.crossattention.self.value)], 0)
@@ -316,7 +317,8 @@ class TagHead(nn.Module):
             fused_kv = (_FusedKVProjection.apply(tag_embeds.to(torch.bfloat16).contiguous(), w, bcat, 2 * len(layers),
                                                  self._k, gbuf), gbuf)
         K_ = _kernels(self._k)
-        fused_ln = (self.fuse_ln and amp_bf16 and hasattr(K_, "ln_res_fwd") and K_.supports_ln_res(TAG_HIDDEN))
+        fused_ln = (self.fuse_ln and (amp_bf16 or (hooked and tag_embeds.dtype == torch.bfloat16))
+                    and hasattr(K_, "ln_res_fwd") and K_.supports_ln_res(TAG_HIDDEN))
         for li, layer in enumerate(layers):
             ca = layer.crossattention
             if h is None:
